@@ -1,0 +1,125 @@
+/*
+ * stemseg_b200 -- C ABI of the B200-native (sm_100a) STEm-Seg hot path.
+ *
+ * The reference (sabarim/STEm-Seg) is pure Python/PyTorch and has no FFI boundary of its own;
+ * its seams for this path are Python call sites.  Every entry point below names the reference call site whose
+ * arithmetic it replaces (paths relative to the reference root).  The Python host layer in stemseg_b200/*.py
+ * mirrors the reference's classes (same names, arguments, state_dict keys, error behaviour) on top of this ABI;
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every *device* pointer is documented as such; no allocation inside the
+ *     library -- the caller owns every buffer, workspace sizes come from the *_workspace_bytes queries;
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*); functions return
+ *     without synchronising unless stated;
+ *   - return 0 on success, a negative STEMSEG_ERR_* code otherwise; stemseg_last_error() gives the message
+ *     (thread-local);
+ *   - tensors: "NDHWC" means [N][T][H][W][C] row-major with C innermost ("channels-last-3d").
+ */
+#ifndef STEMSEG_B200_H_
+#define STEMSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEMSEG_OK 0
+#define STEMSEG_ERR_INVALID_ARGUMENT (-1)
+#define STEMSEG_ERR_CUDA (-2)
+#define STEMSEG_ERR_UNSUPPORTED (-3)
+#define STEMSEG_ERR_WORKSPACE (-4)
+
+#define STEMSEG_MAX_EMBEDDING_DIMS 16
+#define STEMSEG_MAX_INSTANCES 64
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* stemseg_last_error(void);
+/* ABI version of the loaded library (bumped on any signature change). */
+int32_t stemseg_abi_version(void);
+/* 0 if the current CUDA device is sm_100 (B200), else STEMSEG_ERR_UNSUPPORTED. Never falls back to anything. */
+int32_t stemseg_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sequential Gaussian-bandwidth clustering
+ *   replaces SequentialClustering._process            stemseg/inference/clusterers.py:60-166
+ *            ._get_next_instance_center               stemseg/inference/clusterers.py:168-175
+ *            compute_distance / distances_to_prob     stemseg/inference/clusterers.py:53-58
+ * One persistent cooperative kernel runs every iteration (masked grid-wide argmax of seediness -> centre ->
+ * distances -> threshold -> label write) plus the secondary assignment on the device with no host round trip.
+ *
+ * Probability thresholds arrive in the distance domain: d_primary / d_secondary are the largest fp32 distances
+ * d with exp(-0.5 d) > p  (clusterers.py:53-54,136-138,156-157; the map is monotone), computed on the host by
+ * stemseg_prob_threshold_to_distance(); the kernel tests `d <= d_*` and contains no exp.
+ *
+ * Result layout of `meta` (device, 4-byte words, fetched by the caller with one D2H copy):
+ *   word 0            K  = number of clusters created                    (len(instance_labels), clusterers.py:121)
+ *   word 1            exit reason: 0 loop ran max_instances times, 1 no unassigned point left (clusterers.py:109),
+ *                                  2 best seediness < min_seediness_prob (clusterers.py:116)
+ *   word 2..3         reserved
+ *   then int32  seed_index[max_instances]       index of the seed point of cluster k
+ *   then float  centers[max_instances][E]       instance_centers (clusterers.py:124)
+ *   then float  bandwidths[max_instances][E]    cat(bandwidth[seed], free_dim_bandwidths) (clusterers.py:119);
+ *                                               instance_stds = sqrt(clamp(1/bw, 1e-8)) is left to the host
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct StemsegClusterParams {
+    int64_t n_points;            /* N                                                                          */
+    int32_t embedding_dims;      /* E  (1..STEMSEG_MAX_EMBEDDING_DIMS)                                          */
+    int32_t n_free_dims;         /* f; bandwidths has E-f columns, the last f come from free_dim_bandwidths     */
+    float free_dim_bandwidths[STEMSEG_MAX_EMBEDDING_DIMS]; /* 1/std^2, clusterers.py:100-102                   */
+    float d_primary;             /* see above                                                                  */
+    float d_secondary;
+    float min_seediness_prob;    /* compared in fp32 like torch does (clusterers.py:116)                       */
+    int32_t max_instances;       /* clusterers.py:36 (default 20), <= STEMSEG_MAX_INSTANCES                    */
+    int64_t cluster_label_start; /* clusterers.py:60                                                           */
+} StemsegClusterParams;
+
+size_t stemseg_seq_cluster_meta_words(int32_t embedding_dims, int32_t max_instances);
+int32_t stemseg_seq_cluster_workspace_bytes(const StemsegClusterParams* params, size_t* bytes);
+/*
+ * embeddings  device float [N][E]      (row-major, contiguous)       clusterers.py:61
+ * bandwidths  device float [N][E-f]    already activated (exp*10, inference_model.py:148)
+ * seediness   device float [N]         (the reference's [N,1] squeezed, clusterers.py:84)
+ * labels      device int64 [N]  out    final labels, -1 = unassigned (clusterers.py:96,143,159)
+ * primary     device int32 [N]  out    ordinal k of the cluster that claimed the point in the primary pass, -1 if
+ *                                      none (instance_masks[k] == (primary == k), clusterers.py:145-146)
+ * meta        device words      out    see above
+ * Precondition N >= 1 (the N == 0 early return of clusterers.py:62-69 is host logic).
+ */
+int32_t stemseg_seq_cluster(const float* embeddings, const float* bandwidths, const float* seediness,
+                            const StemsegClusterParams* params, int64_t* labels, int32_t* primary, void* meta,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host helper: largest fp32 d >= 0 with fl32(exp(-0.5 d)) > fl32(p); -1 if none, +inf if every d qualifies. */
+float stemseg_prob_threshold_to_distance(double prob_threshold);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Foreground compaction + gather
+ *   replaces masks_to_coord_list                       stemseg/inference/online_chainer.py:11-22
+ *            the gather in cluster_subsequence         stemseg/inference/online_chainer.py:258-281
+ * stemseg_fg_compact: ordered stream compaction of a [T][H*W] uint8 mask (non-zero = foreground) into linear
+ * voxel indices t*H*W + y*W + x, frame-major / row-major like torch.nonzero, plus per-frame counts.
+ * stemseg_fg_gather: channel-first maps -> point-major rows for the n compacted voxels.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t stemseg_fg_compact_workspace_bytes(int64_t n_frames, int64_t frame_voxels);
+/*
+ * mask          device uint8 [T][HW]
+ * indices       device int32 [T*HW] out (first total entries valid)
+ * frame_counts  device int32 [T+1]  out (counts per frame, then the total)
+ */
+int32_t stemseg_fg_compact(const uint8_t* mask, int64_t n_frames, int64_t frame_voxels, int32_t* indices,
+                           int32_t* frame_counts, void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * src       device float [C][T*HW] channel-first map, channel stride `channel_stride` elements
+ * indices   device int32 [n]
+ * dst       device float [n][C] out
+ */
+int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, int32_t channels, const int32_t* indices,
+                          int64_t n, float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEMSEG_B200_H_ */

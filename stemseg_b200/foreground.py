@@ -1,0 +1,101 @@
+"""Foreground compaction + gather on the device.
+
+Replaces ``masks_to_coord_list`` (stemseg/inference/online_chainer.py:11-22) and the gather half of
+``OnlineChainer.cluster_subsequence`` (online_chainer.py:258-281): T ``nonzero`` syncs + 3T advanced-index gathers +
+3 ``cat`` become one ordered stream compaction and one gather per map.
+"""
+import torch
+
+from stemseg_b200 import _lib
+
+
+class ForegroundIndex(object):
+    """Ordered foreground voxel list of a [T,H,W] mask.
+
+    ``indices``: int32 [N] device tensor of linear voxel ids t*H*W + y*W + x in frame-major / row-major order (the
+    order torch.nonzero produces per frame); ``frame_counts``: python list of per-frame counts (one D2H copy).
+    ``coord_list()`` reproduces the reference's list(T) of (y, x) index tuples (online_chainer.py:11-22).
+    """
+
+    def __init__(self, indices, frame_counts, shape):
+        self.indices = indices
+        self.frame_counts = frame_counts
+        self.shape = tuple(shape)
+
+    @property
+    def num_points(self):
+        return int(self.indices.shape[0])
+
+    def frame_slice(self, frames):
+        """ForegroundIndex restricted to (and re-based on) the given ascending frame numbers."""
+        t, h, w = self.shape
+        offsets = [0]
+        for c in self.frame_counts:
+            offsets.append(offsets[-1] + c)
+        parts, counts = [], []
+        for j, f in enumerate(frames):
+            seg = self.indices[offsets[f]:offsets[f + 1]]
+            parts.append(seg + (j - f) * h * w)
+            counts.append(self.frame_counts[f])
+        idx = torch.cat(parts) if parts else self.indices[:0]
+        return ForegroundIndex(idx.to(torch.int32), counts, (len(frames), h, w))
+
+    def coord_list(self):
+        t, h, w = self.shape
+        out, start = [], 0
+        for f, c in enumerate(self.frame_counts):
+            lin = self.indices[start:start + c].long() - f * h * w
+            out.append((torch.div(lin, w, rounding_mode="floor"), lin % w))
+            start += c
+        return out
+
+
+@torch.no_grad()
+def compact_foreground(masks):
+    """masks: [T,H,W] tensor on a CUDA device, any integer/bool dtype (non-zero = foreground)."""
+    if masks.dim() != 3:
+        raise ValueError("expected a [T,H,W] mask, got shape %s" % (tuple(masks.shape),))
+    if not masks.is_cuda:
+        raise ValueError("compact_foreground needs a CUDA tensor; there is no CPU path")
+    t, h, w = masks.shape
+    if masks.dtype == torch.bool:
+        m = masks.contiguous().view(torch.uint8)
+    elif masks.dtype == torch.uint8:
+        m = masks.contiguous()
+    else:
+        m = (masks != 0).contiguous().view(torch.uint8)
+    if t * h * w == 0:
+        return ForegroundIndex(torch.zeros(0, dtype=torch.int32, device=masks.device), [0] * t, (t, h, w))
+    lib = _lib.load()
+    with torch.cuda.device(masks.device):
+        ws_bytes = lib.stemseg_fg_compact_workspace_bytes(t, h * w)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
+        indices = torch.empty(t * h * w, dtype=torch.int32, device=masks.device)
+        counts = torch.empty(t + 1, dtype=torch.int32, device=masks.device)
+        _lib.check(lib.stemseg_fg_compact(_lib.ptr(m), t, h * w, _lib.ptr(indices), _lib.ptr(counts), _lib.ptr(ws),
+                                          ws_bytes, _lib.stream_ptr()))
+        counts_host = counts.cpu().tolist()          # one sync (the reference syncs once per frame)
+    return ForegroundIndex(indices[:counts_host[-1]], counts_host[:-1], (t, h, w))
+
+
+@torch.no_grad()
+def gather_points(channel_first_map, fg_index):
+    """channel_first_map: [C,T,H,W] fp32 CUDA tensor -> [N,C] rows for the foreground voxels (online_chainer.py:265-281)."""
+    x = channel_first_map
+    if x.dim() != 4 or tuple(x.shape[1:]) != fg_index.shape:
+        raise ValueError("map shape %s does not match mask shape %s" % (tuple(x.shape), fg_index.shape))
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("gather_points needs an fp32 CUDA tensor")
+    c = x.shape[0]
+    inner = x.shape[1] * x.shape[2] * x.shape[3]
+    if not x[0].is_contiguous() or (c > 1 and x.stride(0) < inner):
+        x = x.contiguous()
+    n = fg_index.num_points
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c,
+                                         _lib.ptr(fg_index.indices), n, _lib.ptr(out), _lib.stream_ptr()))
+    return out
