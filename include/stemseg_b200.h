@@ -119,6 +119,66 @@ int32_t stemseg_fg_compact(const uint8_t* mask, int64_t n_frames, int64_t frame_
 int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, int32_t channels, const int32_t* indices,
                           int64_t n, float* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * 3-D decoder heads (SqueezingExpandDecoder x3)
+ *   replaces the forward of  stemseg/modeling/embedding_decoder.py:101-145
+ *                            stemseg/modeling/seediness_decoder.py:82-112
+ *                            stemseg/modeling/semseg_decoder.py:91-116
+ * Internal layout: activations are NDHWC bf16 "planes": plane 0 = bf16(x), plane 1 = bf16(x - plane0) when
+ * planes == 2 (fp32-parity mode: three tensor-core products hi*hi + hi*lo + lo*hi), plane 0 only when
+ * planes == 1 (bf16 mode).  Plane p of a tensor starts p * numel elements after plane 0.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* NCTHW fp32 (any n/c/t strides, H*W contiguous) -> NDHWC bf16 planes.  Replaces the permute / stack copies of
+ * restore_temporal_dimension (model_builder.py:84-99) and torch.stack(.., 2) (inference_model.py:112-119). */
+int32_t stemseg_pack_activation(const float* src, int64_t stride_n, int64_t stride_c, int64_t stride_t, int32_t n,
+                                int32_t c, int32_t t, int32_t hw, void* dst_planes, int32_t planes, void* stream);
+
+/* nn.Conv3d / 1x1x1 weight [cout][cin_total][taps] fp32 (state_dict layout, taps = 27 or 1) -> K-major bf16 planes
+ * [rows_total][taps][cin_count] at rows [row_begin, row_begin+cout), input channels [cin_begin, +cin_count).
+ * Row offsets let several heads share one GEMM N dimension; channel ranges split the concat-conv weights
+ * (embedding_decoder.py:68,74,80) into their upsampled / skip halves. */
+int32_t stemseg_pack_conv_weight(const float* src, int32_t cout, int32_t cin_total, int32_t cin_begin,
+                                 int32_t cin_count, int32_t taps, void* dst_planes, int32_t row_begin,
+                                 int32_t rows_total, int32_t planes, void* stream);
+
+typedef struct StemsegConvShape {
+    int32_t n, t, h, w;      /* output volume == input volume (stride 1, zero padding 1 for kernel_size 3)        */
+    int32_t cin, cout;       /* multiples of 32                                                                 */
+    int32_t kernel_size;     /* 3 (3x3x3, embedding_decoder.py:21) or 1 (1x1x1 merge, embedding_decoder.py:68)  */
+    int32_t planes;          /* 1 or 2                                                                          */
+} StemsegConvShape;
+
+/* out[n][t][h][w][cout] (fp32) = conv(act) + bias.  tcgen05 implicit GEMM, TMA im2col, fp32 accumulation in TMEM.
+ * max_ctas > 0 caps the persistent grid (used to run independent branches concurrently on separate streams). */
+int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias, float* out,
+                                   const StemsegConvShape* shape, int32_t max_ctas, void* stream);
+
+/* GroupNorm statistics of an NDHWC fp32 tensor: mean_rstd[n][c/channels_per_group][2] (biased variance, eps inside
+ * the sqrt) -- nn.GroupNorm(32, C) (model_builder.py:34). Deterministic (fixed reduction order). */
+size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
+int32_t stemseg_group_norm_stats(const float* x, int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
+                                 float eps, float* mean_rstd, void* workspace, size_t workspace_bytes, void* stream);
+
+/* relu(group_norm(x)) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
+ * (embedding_decoder.py:22-24; common.py:8-24).  mean_rstd/gamma/beta all NULL = no normalisation. */
+int32_t stemseg_norm_relu_pool(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                               int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t channels_per_group,
+                               int32_t pool, void* dst_planes, int32_t planes, void* stream);
+
+/* dst = z + trilinear_upsample(y_low, (t_scale, 2, 2), align_corners=False) -> bf16 planes; z is [n][t][h][w][c],
+ * y_low [n][t/t_scale][h/2][w/2][c] (common.py:69-78; conv1x1(cat(up(x), f)) == up(W_a x) + W_b f). */
+int32_t stemseg_upsample_add(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h, int32_t w,
+                             int32_t c, int32_t t_scale, void* dst_planes, int32_t planes, void* stream);
+
+/* Output heads on x = z + upsample(y_low): n_out 1x1x1 outputs with activation[j] (0 identity, 1 tanh(0.25 v),
+ * 2 sigmoid) and coordinate[j] (0 none, 1 t, 2 y, 3 x) offsets; out is channels-first [n][n_out][t][h][w] fp32
+ * (embedding_decoder.py:131-145, embedding_utils.py:29-120, seediness_decoder.py:112, semseg_decoder.py:116). */
+int32_t stemseg_head_output(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h, int32_t w,
+                            int32_t c, int32_t t_scale, const float* out_weight, const float* out_bias,
+                            const int32_t* activation, const int32_t* coordinate, int32_t n_out, float time_scale,
+                            float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,11 @@ class StemsegClusterParams(ctypes.Structure):
     ]
 
 
+class StemsegConvShape(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("t", c_int32), ("h", c_int32), ("w", c_int32), ("cin", c_int32), ("cout", c_int32),
+                ("kernel_size", c_int32), ("planes", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/stemseg_b200.h declares (tests check the two agree)
 PROTOTYPES = {
     "stemseg_last_error": (ctypes.c_char_p, []),
@@ -41,6 +46,21 @@ PROTOTYPES = {
     "stemseg_fg_compact_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "stemseg_fg_compact": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "stemseg_pack_activation": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                          c_void_p, c_int32, c_void_p]),
+    "stemseg_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                           c_int32, c_int32, c_void_p]),
+    "stemseg_conv3d_bf16_planes": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                             ctypes.POINTER(StemsegConvShape), c_int32, c_void_p]),
+    "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]),
+    "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                         c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "stemseg_upsample_add": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p, c_int32, c_void_p]),
+    "stemseg_head_output": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p]),
 }
 
 

@@ -1,0 +1,535 @@
+// K1: 3x3x3 / 1x1x1 convolution over NDHWC bf16 planes as a tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces nn.Conv3d(C, C', 3, padding=1) (stemseg/modeling/embedding_decoder.py:21-57 and the same lines of
+// seediness_decoder.py / semseg_decoder.py) and the 1x1x1 merge convs (embedding_decoder.py:68,74,80).
+//
+//   D[voxel, cout] = sum_{tap, cin} A[voxel + tap, cin] * W[cout, tap, cin]          (fp32 accumulate in TMEM)
+//
+// * M tile = a (tt x th x tw) = 128-voxel box of one sample.  The im2col gather is done by TMA: one tiled 5-D
+//   box load per (tap, 64/32-channel chunk) with the start coordinate shifted by the tap offset; out-of-bounds
+//   elements (the zero padding, and ragged tile edges) are zero-filled by the TMA unit.  The box lands in shared
+//   memory exactly as the canonical K-major SWIZZLE_128B/64B UMMA operand (one voxel = one 128/64-byte row).
+// * B tile = [BLOCK_N couts][BLOCK_K] slab of the pre-packed weight matrix [Cout][tap][Cin] (K-major).
+// * fp32 parity mode (PLANES == 2): activations and weights are split x = hi + lo into two bf16 planes and three
+//   MMAs (hi*hi, hi*lo, lo*hi) accumulate into the same TMEM tile -- ~2^-17 relative operand error instead of
+//   bf16's 2^-9 (measured 1.2e-5 norm-wise on the variance logits, budget 1e-4).  PLANES == 1 is the plain bf16 mode.
+// * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (single elected
+//   thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> +bias -> fp32 NDHWC store).  Two TMEM accumulator
+//   stages so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace stemseg {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kUmmaK = 16;                 // bf16
+constexpr int kNumThreads = 192;           // 6 warps
+constexpr int kNumEpilogueThreads = 128;
+constexpr int kAccStages = 2;
+
+struct ConvTcParams {
+    int n, t, h, w;
+    int cin, cout;
+    int ntaps;                 // 27 (3x3x3, pad 1) or 1
+    int tt, th, tw;            // voxel box of one M tile (tt*th*tw == 128)
+    int tiles_t, tiles_h, tiles_w;
+    int n_tiles_n;
+    int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n
+    float* out;                // [n][t][h][w][cout] fp32
+    const float* bias;         // [cout] or nullptr
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 24)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// tcgen05.commit: the mbarrier is arrived on once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of ROW_BYTES (= swizzle span) bytes, 8-row groups contiguous.
+// Descriptor fields (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30) (unused for a
+// single swizzle atom along K), SBO>>4 [32,46) = 8 rows * ROW_BYTES, version=1 [46,48), layout type [61,64).
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = ROW_BYTES == 128 ? 2ull : (ROW_BYTES == 64 ? 4ull : 6ull);   // SW128 / SW64 / SW32
+    constexpr uint64_t sbo = (8ull * ROW_BYTES) >> 4;
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Instruction descriptor (InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1, K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29).
+template <int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N>
+constexpr int tmem_columns() {
+    return kAccStages * BLOCK_N <= 32 ? 32 : kAccStages * BLOCK_N <= 64 ? 64 : kAccStages * BLOCK_N <= 128 ? 128
+           : kAccStages * BLOCK_N <= 256 ? 256 : 512;
+}
+
+template <int BLOCK_N, int BLOCK_K, int PLANES>
+constexpr int stage_bytes() {
+    return PLANES * (kBlockM * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2);
+}
+
+struct TileCoord {
+    int n, t0, h0, w0, n_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile) {
+    TileCoord c;
+    c.n_tile = tile % p.n_tiles_n;
+    int m = tile / p.n_tiles_n;
+    c.w0 = (m % p.tiles_w) * p.tw;
+    m /= p.tiles_w;
+    c.h0 = (m % p.tiles_h) * p.th;
+    m /= p.tiles_h;
+    c.t0 = (m % p.tiles_t) * p.tt;
+    c.n = m / p.tiles_t;
+    return c;
+}
+
+template <int BLOCK_N, int BLOCK_K, int PLANES, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant__ CUtensorMap a_map1,
+               const __grid_constant__ CUtensorMap b_map0, const __grid_constant__ CUtensorMap b_map1,
+               const ConvTcParams p) {
+    constexpr int ROW_BYTES = BLOCK_K * 2;
+    constexpr int A_BYTES = kBlockM * ROW_BYTES;
+    constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+    constexpr int STAGE_BYTES = stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
+    constexpr int TMEM_COLS = tmem_columns<BLOCK_N>();
+    static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K must equal one swizzle atom (64 or 32 bf16)");
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+    static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int k_chunks = p.cin / BLOCK_K;
+    const int num_k_blocks = p.ntaps * k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&a_map0);
+        prefetch_tmap(&b_map0);
+        if (PLANES == 2) {
+            prefetch_tmap(&a_map1);
+            prefetch_tmap(&b_map1);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            mbar_init(tmem_full_bar + a, 1);
+            mbar_init(tmem_empty_bar + a, kNumEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // whole warp: allocate the accumulator columns, publish the base address through smem
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    const int tap = kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
+                    int dt = 0, dh = 0, dw = 0;
+                    if (p.ntaps == 27) {
+                        dt = tap / 9 - 1;
+                        dh = (tap / 3) % 3 - 1;
+                        dw = tap % 3 - 1;
+                    }
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+                    tma_load_5d(&a_map0, full_bar + stage, st, c0, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n);
+                    if (PLANES == 2)
+                        tma_load_5d(&a_map1, full_bar + stage, st + A_BYTES, c0, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n);
+                    uint8_t* sb = st + PLANES * A_BYTES;
+                    const int kcoord = tap * p.cin + c0;
+                    tma_load_2d(&b_map0, full_bar + stage, sb, kcoord, tc.n_tile * BLOCK_N);
+                    if (PLANES == 2) tma_load_2d(&b_map1, full_bar + stage, sb + B_BYTES, kcoord, tc.n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(full_bar + stage, phase);                // TMA bytes have landed
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b0 = a0 + PLANES * A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / kUmmaK; ++k) {
+                        const uint32_t koff = k * kUmmaK * 2;      // bytes inside the swizzle atom
+                        const uint64_t a_hi = make_kmajor_desc<ROW_BYTES>(a0 + koff);
+                        const uint64_t b_hi = make_kmajor_desc<ROW_BYTES>(b0 + koff);
+                        umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (PLANES == 2) {
+                            const uint64_t a_lo = make_kmajor_desc<ROW_BYTES>(a0 + A_BYTES + koff);
+                            const uint64_t b_lo = make_kmajor_desc<ROW_BYTES>(b0 + B_BYTES + koff);
+                            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar + stage);                               // frees the smem stage
+                    if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar + acc); // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;          // accumulator row == voxel index inside the tile box
+        const int dw = row % p.tw, dh = (row / p.tw) % p.th, dt = row / (p.tw * p.th);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile);
+            const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
+            const bool valid = t < p.t && h < p.h && w < p.w;
+            float* out_row = p.out + ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
+                                      static_cast<size_t>(tc.n_tile) * BLOCK_N);
+            const float* bias = p.bias ? p.bias + tc.n_tile * BLOCK_N : nullptr;
+            mbar_wait(tmem_full_bar + acc, acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c, v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 32; q += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[q + 0]);
+                        o.y = __uint_as_float(v[q + 1]);
+                        o.z = __uint_as_float(v[q + 2]);
+                        o.w = __uint_as_float(v[q + 3]);
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(out_row + c + q) = o;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tmem_empty_bar + acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || ptr == nullptr)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, const ConvTcParams& p, int block_k) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return STEMSEG_ERR_CUDA;
+    }
+    const cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.cin), static_cast<cuuint64_t>(p.w),
+                                static_cast<cuuint64_t>(p.h), static_cast<cuuint64_t>(p.t),
+                                static_cast<cuuint64_t>(p.n)};
+    const cuuint64_t c2 = static_cast<cuuint64_t>(p.cin) * 2;
+    const cuuint64_t strides[4] = {c2, c2 * p.w, c2 * p.w * p.h, c2 * p.w * p.h * p.t};
+    const cuuint32_t box[5] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(p.tw),
+                               static_cast<cuuint32_t>(p.th), static_cast<cuuint32_t>(p.tt), 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(activation) failed with CUresult %d", static_cast<int>(r));
+        return STEMSEG_ERR_CUDA;
+    }
+    return STEMSEG_OK;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* base, int64_t k_total, int64_t cout_rows, int block_k,
+                      int block_n) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return STEMSEG_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(cout_rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(block_n)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", static_cast<int>(r));
+        return STEMSEG_ERR_CUDA;
+    }
+    return STEMSEG_OK;
+}
+
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BLOCK_N, int BLOCK_K, int PLANES>
+constexpr int stages_for() {
+    constexpr int s = kSmemBudget / stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
+    return s > 8 ? 8 : s;
+}
+
+template <int BLOCK_N, int BLOCK_K, int PLANES>
+int launch_variant(const CUtensorMap* maps, const ConvTcParams& p, int max_ctas, cudaStream_t stream) {
+    constexpr int STAGES = stages_for<BLOCK_N, BLOCK_K, PLANES>();
+    static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
+    constexpr int smem_bytes = STAGES * stage_bytes<BLOCK_N, BLOCK_K, PLANES>() + 1024 /*align*/ + 256 /*barriers*/;
+    auto kernel = conv_tc_kernel<BLOCK_N, BLOCK_K, PLANES, STAGES>;
+    SS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int grid = device_sm_count();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kernel<<<grid, kNumThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+template <int BLOCK_K, int PLANES>
+int launch_by_n(int block_n, const CUtensorMap* maps, const ConvTcParams& p, int max_ctas, cudaStream_t stream) {
+    switch (block_n) {
+        case 256: return launch_variant<256, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
+        case 128: return launch_variant<128, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
+        case 64: return launch_variant<64, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
+        case 32: return launch_variant<32, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
+    }
+    set_error("conv_tc: unsupported BLOCK_N %d", block_n);
+    return STEMSEG_ERR_UNSUPPORTED;
+}
+
+// choose the 128-voxel box (tt, th, tw) with the least padded volume (ties: prefer wide w, then h)
+void choose_box(int t, int h, int w, int* tt, int* th, int* tw) {
+    long long best = -1;
+    for (int a = 1; a <= 128; a *= 2)
+        for (int b = 1; a * b <= 128; b *= 2) {
+            const int c = 128 / (a * b);
+            // a = tt, b = th, c = tw
+            const long long vol = 1ll * ((t + a - 1) / a) * ((h + b - 1) / b) * ((w + c - 1) / c);
+            const long long score = vol * 1024 - c * 8 - b;     // fewer tiles first, then wider rows
+            if (best < 0 || score < best) {
+                best = score;
+                *tt = a; *th = b; *tw = c;
+            }
+        }
+}
+
+}  // namespace
+}  // namespace stemseg
+
+using namespace stemseg;
+
+extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias,
+                                              float* out, const StemsegConvShape* s, int32_t max_ctas,
+                                              void* stream_) {
+    SS_REQUIRE(s != nullptr && act_planes && weight_planes && out, "conv3d: null pointer");
+    SS_REQUIRE(s->planes == 1 || s->planes == 2, "conv3d: planes must be 1 or 2");
+    SS_REQUIRE(s->kernel_size == 3 || s->kernel_size == 1, "conv3d: kernel_size must be 1 or 3");
+    SS_REQUIRE(s->n >= 1 && s->t >= 1 && s->h >= 1 && s->w >= 1, "conv3d: empty volume");
+    SS_REQUIRE(s->cin >= 32 && s->cin % 32 == 0, "conv3d: cin must be a positive multiple of 32 (got %d)", s->cin);
+    SS_REQUIRE(s->cout >= 32 && s->cout % 32 == 0, "conv3d: cout must be a positive multiple of 32 (got %d)", s->cout);
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(act_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight_planes) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+               "conv3d: pointers must be 16-byte aligned");
+    int rc = require_sm100();
+    if (rc != STEMSEG_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    ConvTcParams p;
+    p.n = s->n; p.t = s->t; p.h = s->h; p.w = s->w;
+    p.cin = s->cin; p.cout = s->cout;
+    p.ntaps = s->kernel_size == 3 ? 27 : 1;
+    choose_box(p.t, p.h, p.w, &p.tt, &p.th, &p.tw);
+    p.tiles_t = (p.t + p.tt - 1) / p.tt;
+    p.tiles_h = (p.h + p.th - 1) / p.th;
+    p.tiles_w = (p.w + p.tw - 1) / p.tw;
+    const int block_n = s->cout % 256 == 0 ? 256 : s->cout % 128 == 0 ? 128 : s->cout % 64 == 0 ? 64 : 32;
+    p.n_tiles_n = s->cout / block_n;
+    const long long tiles = 1ll * p.n * p.tiles_t * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    SS_REQUIRE(tiles < 0x7FFFFFFFll, "conv3d: too many tiles");
+    p.num_tiles = static_cast<int>(tiles);
+    p.out = out;
+    p.bias = bias;
+
+    // BLOCK_K: 64 channels (SWIZZLE_128B) when the stage still leaves >= 3 pipeline stages, else 32 (SWIZZLE_64B)
+    int block_k = (s->cin % 64 == 0) ? 64 : 32;
+    if (block_k == 64 && s->planes == 2 && block_n == 256) block_k = 32;
+
+    const size_t act_plane_bytes = static_cast<size_t>(p.n) * p.t * p.h * p.w * p.cin * 2;
+    const int64_t k_total = static_cast<int64_t>(p.ntaps) * p.cin;
+    const size_t w_plane_bytes = static_cast<size_t>(k_total) * p.cout * 2;
+    CUtensorMap maps[4];
+    const uint8_t* a = static_cast<const uint8_t*>(act_planes);
+    const uint8_t* b = static_cast<const uint8_t*>(weight_planes);
+    for (int pl = 0; pl < 2; ++pl) {
+        const int src = pl < s->planes ? pl : 0;
+        rc = encode_act_map(&maps[pl], a + src * act_plane_bytes, p, block_k);
+        if (rc != STEMSEG_OK) return rc;
+        rc = encode_weight_map(&maps[2 + pl], b + src * w_plane_bytes, k_total, p.cout, block_k, block_n);
+        if (rc != STEMSEG_OK) return rc;
+    }
+    if (s->planes == 2)
+        return block_k == 64 ? launch_by_n<64, 2>(block_n, maps, p, max_ctas, stream)
+                             : launch_by_n<32, 2>(block_n, maps, p, max_ctas, stream);
+    return block_k == 64 ? launch_by_n<64, 1>(block_n, maps, p, max_ctas, stream)
+                         : launch_by_n<32, 1>(block_n, maps, p, max_ctas, stream);
+}

@@ -1,0 +1,547 @@
+// Decoder-head kernels around the tcgen05 convolution (sm_100a): operand packing, GroupNorm statistics,
+// GroupNorm+ReLU(+AvgPool3d) apply, trilinear upsample-add, and the fused output heads.
+//
+// All of these are HBM-bound elementwise / small-stencil passes over NDHWC tensors: vectorised (float4 / bf16x4)
+// accesses along the channel axis, no shared-memory staging needed except for the NCTHW -> NDHWC transpose.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace stemseg {
+namespace {
+
+// ---- fp32 -> bf16 planes: x ~= hi + lo (lo = bf16(x - hi)), round-to-nearest-even both times ------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct alignas(8) bf16x4 {
+    __nv_bfloat16 v[4];
+};
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi_plane, size_t plane_elems, int planes, size_t off,
+                                              const float (&x)[4]) {
+    bf16x4 h, l;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_bf16(x[k], h.v[k], l.v[k]);
+    *reinterpret_cast<bf16x4*>(hi_plane + off) = h;
+    if (planes == 2) *reinterpret_cast<bf16x4*>(hi_plane + plane_elems + off) = l;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K0: [N][C][T][HW] fp32 (strides sn, sc, st; HW contiguous) -> planes [P][N][T][HW][C] bf16
+// Replaces the permute / stack "temporal fusion" copies (model_builder.py:84-99, inference_model.py:112-119).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPackC = 64, kPackS = 32;
+
+__global__ void __launch_bounds__(256) pack_ncthw_kernel(const float* __restrict__ src, long long sn, long long sc,
+                                                         long long st, int c, int t, int hw,
+                                                         __nv_bfloat16* __restrict__ dst, size_t plane_elems,
+                                                         int planes) {
+    __shared__ float tile[kPackC][kPackS + 1];
+    const int s0 = blockIdx.x * kPackS, c0 = blockIdx.y * kPackC;
+    const int nt = blockIdx.z, n = nt / t, tt = nt % t;
+    const float* base = src + n * sn + tt * st;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int i = 0; i < kPackC / 8; ++i) {
+        const int cc = c0 + ty + 8 * i, s = s0 + tx;
+        tile[ty + 8 * i][tx] = (cc < c && s < hw) ? __ldg(base + cc * sc + s) : 0.f;
+    }
+    __syncthreads();
+    // each thread writes 2 channels of one voxel: 32 lanes x 2 = 64 channels = one 128-byte row segment
+#pragma unroll
+    for (int i = 0; i < kPackS / 8; ++i) {
+        const int s = s0 + ty + 8 * i, cc = c0 + 2 * tx;
+        if (s < hw && cc < c) {
+            const size_t off = ((static_cast<size_t>(nt) * hw + s) * c) + cc;
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(tile[2 * tx][ty + 8 * i], h0, l0);
+            split_bf16(tile[2 * tx + 1][ty + 8 * i], h1, l1);
+            *reinterpret_cast<__nv_bfloat162*>(dst + off) = __nv_bfloat162(h0, h1);
+            if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(dst + plane_elems + off) = __nv_bfloat162(l0, l1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: torch [Cout][Cin_total][taps] fp32 -> planes [P][rows_total][taps][cin_count] bf16 (K-major)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int cin_total, int cin_begin,
+                                   int cin_count, int taps, __nv_bfloat16* __restrict__ dst, int row_begin,
+                                   size_t plane_elems, int planes) {
+    const long long total = 1ll * cout * taps * cin_count;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int ci = static_cast<int>(i % cin_count);
+        const int tap = static_cast<int>((i / cin_count) % taps);
+        const int co = static_cast<int>(i / (1ll * cin_count * taps));
+        const float x = src[(static_cast<size_t>(co) * cin_total + cin_begin + ci) * taps + tap];
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        const size_t off = (static_cast<size_t>(row_begin + co) * taps + tap) * cin_count + ci;
+        dst[off] = h;
+        if (planes == 2) dst[plane_elems + off] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2a: per-channel partial sums of an NDHWC fp32 tensor; K2b: finalize per (sample, group) mean / rstd.
+// Replaces the statistics pass of nn.GroupNorm(32, C) (model_builder.py:34; embedding_decoder.py:22,...).
+// Deterministic: fixed chunking, fixed reduction order, final combination in double.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStatsChunk = 2048;     // voxels per block
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, long long spatial, int c,
+                                                         float* __restrict__ partial /*[n][chunks][c][2]*/,
+                                                         int chunks) {
+    extern __shared__ float s_acc[];                 // [rows][c][2]
+    const int quads = c / 4;
+    const int rows = blockDim.x / quads;
+    const int q = threadIdx.x % quads, r = threadIdx.x / quads;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const long long v0 = 1ll * chunk * kStatsChunk;
+    long long v1 = v0 + kStatsChunk;
+    if (v1 > spatial) v1 = spatial;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+        const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * c) + q;
+        for (long long v = v0 + r; v < v1; v += rows) {
+            const float4 a = __ldg(base + v * quads);
+            s[0] += a.x; ss[0] += a.x * a.x;
+            s[1] += a.y; ss[1] += a.y * a.y;
+            s[2] += a.z; ss[2] += a.z * a.z;
+            s[3] += a.w; ss[3] += a.w * a.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s_acc[(r * c + 4 * q + k) * 2 + 0] = s[k];
+            s_acc[(r * c + 4 * q + k) * 2 + 1] = ss[k];
+        }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int rr = 0; rr < rows; ++rr) {
+            a += s_acc[(rr * c + ch) * 2 + 0];
+            b += s_acc[(rr * c + ch) * 2 + 1];
+        }
+        float* out = partial + ((static_cast<size_t>(n) * chunks + chunk) * c + ch) * 2;
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
+// one block per (group, sample)
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int chunks, int c,
+                                                          int cpg, long long spatial, float eps,
+                                                          float* __restrict__ mean_rstd /*[n][groups][2]*/) {
+    const int g = blockIdx.x, n = blockIdx.y, groups = c / cpg;
+    double s = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < chunks * cpg; i += blockDim.x) {
+        const int chunk = i / cpg, ch = g * cpg + i % cpg;
+        const float* p = partial + ((static_cast<size_t>(n) * chunks + chunk) * c + ch) * 2;
+        s += p[0];
+        ss += p[1];
+    }
+    __shared__ double sh[2][128];
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double cnt = static_cast<double>(spatial) * cpg;
+        const double mean = sh[0][0] / cnt;
+        double var = sh[1][0] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float* o = mean_rstd + (static_cast<size_t>(n) * groups + g) * 2;
+        o[0] = static_cast<float>(mean);
+        o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2c: y = relu((x - mean) * rstd * gamma + beta) [-> AvgPool3d(3, stride (2,1,1), pad 1, divisor 27)] -> bf16 planes
+// Replaces GroupNorm apply + ReLU + AvgPool3d (embedding_decoder.py:22-24; common.py:8-24).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool POOL>
+__global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int n, int t, int h, int w, int c, int cpg, int t_out,
+                                                           __nv_bfloat16* __restrict__ dst, size_t plane_elems,
+                                                           int planes) {
+    const int quads = c / 4;
+    const long long total = 1ll * n * t_out * h * w * quads;
+    const int groups = c / cpg;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int q = static_cast<int>(i % quads);
+        long long v = i / quads;
+        const int ww = static_cast<int>(v % w); v /= w;
+        const int hh = static_cast<int>(v % h); v /= h;
+        const int to = static_cast<int>(v % t_out);
+        const int nn = static_cast<int>(v / t_out);
+        float sc[4], sh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ch = 4 * q + k;
+            float m = 0.f, r = 1.f, g = 1.f, b = 0.f;
+            if (mean_rstd) {
+                const float* mr = mean_rstd + (static_cast<size_t>(nn) * groups + ch / cpg) * 2;
+                m = mr[0]; r = mr[1]; g = gamma[ch]; b = beta[ch];
+            }
+            sc[k] = r * g;
+            sh[k] = b - m * r * g;
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (POOL) {
+            for (int dt = -1; dt <= 1; ++dt) {
+                const int ti = 2 * to + dt;
+                if (ti < 0 || ti >= t) continue;
+                for (int dh = -1; dh <= 1; ++dh) {
+                    const int hi = hh + dh;
+                    if (hi < 0 || hi >= h) continue;
+                    for (int dw = -1; dw <= 1; ++dw) {
+                        const int wi = ww + dw;
+                        if (wi < 0 || wi >= w) continue;
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(
+                                                   x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * c) + q);
+                        acc[0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
+                        acc[1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+                        acc[2] += fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
+                        acc[3] += fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] *= (1.0f / 27.0f);
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(
+                                       x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * c) + q);
+            acc[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
+            acc[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+            acc[2] = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
+            acc[3] = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+        }
+        const size_t off = ((((static_cast<size_t>(nn) * t_out + to) * h + hh) * w + ww) * c) + 4 * q;
+        store_planes4(dst, plane_elems, planes, off, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trilinear (align_corners=False) source taps for integer scale 1 or 2 along one axis (common.py:69-78)
+// ---------------------------------------------------------------------------------------------------------------
+struct Tap {
+    int i0, i1;
+    float w0, w1;
+};
+__device__ __forceinline__ Tap axis_tap(int dst, int scale, int src_size) {
+    Tap tp;
+    if (scale == 1) {
+        tp.i0 = tp.i1 = dst; tp.w0 = 1.f; tp.w1 = 0.f;
+        return tp;
+    }
+    float s = (static_cast<float>(dst) + 0.5f) * 0.5f - 0.5f;       // area_pixel_compute_source_index
+    if (s < 0.f) s = 0.f;
+    tp.i0 = static_cast<int>(s);
+    tp.i1 = tp.i0 + (tp.i0 < src_size - 1 ? 1 : 0);
+    tp.w1 = s - static_cast<float>(tp.i0);
+    tp.w0 = 1.f - tp.w1;
+    return tp;
+}
+
+struct Tri {
+    size_t off[8];
+    float wgt[8];
+};
+__device__ __forceinline__ Tri make_tri(int nn, int to, int ho, int wo, int st, int tl, int hl, int wl, int c) {
+    const Tap a = axis_tap(to, st, tl), b = axis_tap(ho, 2, hl), d = axis_tap(wo, 2, wl);
+    Tri r;
+    const int ti[2] = {a.i0, a.i1}, hi[2] = {b.i0, b.i1}, wi[2] = {d.i0, d.i1};
+    const float tw[2] = {a.w0, a.w1}, hw_[2] = {b.w0, b.w1}, ww[2] = {d.w0, d.w1};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int x = i & 1, y = (i >> 1) & 1, z = i >> 2;
+        r.off[i] = (((static_cast<size_t>(nn) * tl + ti[z]) * hl + hi[y]) * wl + wi[x]) * c;
+        r.wgt[i] = tw[z] * hw_[y] * ww[x];
+    }
+    return r;
+}
+
+// K3b: out = z + upsample(y_low)  -> bf16 planes (input of the next 1x1 merge GEMM)
+// Uses conv1x1(cat(up(x), f)) == up(W_a x) + W_b f (1x1 conv and trilinear interpolation commute).
+__global__ void __launch_bounds__(256) upsample_add_kernel(const float* __restrict__ z, const float* __restrict__ ylow,
+                                                           int n, int t, int h, int w, int c, int st, int tl, int hl,
+                                                           int wl, __nv_bfloat16* __restrict__ dst, size_t plane_elems,
+                                                           int planes) {
+    const int quads = c / 4;
+    const long long total = 1ll * n * t * h * w * quads;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int q = static_cast<int>(i % quads);
+        long long v = i / quads;
+        const int wo = static_cast<int>(v % w); v /= w;
+        const int ho = static_cast<int>(v % h); v /= h;
+        const int to = static_cast<int>(v % t);
+        const int nn = static_cast<int>(v / t);
+        const Tri tr = make_tri(nn, to, ho, wo, st, tl, hl, wl, c);
+        const size_t off = ((((static_cast<size_t>(nn) * t + to) * h + ho) * w + wo) * c) + 4 * q;
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + off));
+        float acc[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (tr.wgt[k] != 0.f) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ylow + tr.off[k]) + q);
+                acc[0] = fmaf(tr.wgt[k], a.x, acc[0]);
+                acc[1] = fmaf(tr.wgt[k], a.y, acc[1]);
+                acc[2] = fmaf(tr.wgt[k], a.z, acc[2]);
+                acc[3] = fmaf(tr.wgt[k], a.w, acc[3]);
+            }
+        }
+        store_planes4(dst, plane_elems, planes, off, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: output heads.  x = z + upsample(y_low) (the conv_4 merge), then J 1x1x1 outputs with per-output activation:
+//   act 0: identity (variance / semseg logits)          embedding_decoder.py:137, semseg_decoder.py:116
+//   act 1: tanh(0.25 v)                                 embedding_decoder.py:132-133
+//   act 2: sigmoid                                      embedding_decoder.py:140, seediness_decoder.py:112
+//   coord 0 none / 1 t / 2 y / 3 x added after the activation (embedding_utils.py:29-120)
+// Output is channels-first [N][J][T][H][W] fp32 -- the layout the callers index (inference_model.py:137-146).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHeadMaxC = 256;
+constexpr int kHeadJChunk = 8;
+
+__device__ __forceinline__ float linspace_value(float end_abs, int steps, int i) {
+    // torch.linspace(-a, a, steps) fp32: start + i*step for the first half, end - (steps-1-i)*step for the second
+    if (steps == 1) return -end_abs;
+    const float step = (end_abs - (-end_abs)) / static_cast<float>(steps - 1);
+    return i < steps / 2 ? (-end_abs + step * static_cast<float>(i)) : (end_abs - step * static_cast<float>(steps - 1 - i));
+}
+
+__global__ void __launch_bounds__(128) head_out_kernel(const float* __restrict__ z, const float* __restrict__ ylow,
+                                                       int n, int t, int h, int w, int c, int st, int tl, int hl,
+                                                       int wl, const float* __restrict__ wout /*[J][c]*/,
+                                                       const float* __restrict__ bout /*[J] or null*/,
+                                                       const int* __restrict__ act, const int* __restrict__ coord,
+                                                       int j_total, float x_abs, float y_abs, float t_abs,
+                                                       float* __restrict__ out) {
+    extern __shared__ float s_w[];          // [J][c] + [J] bias
+    float* s_b = s_w + j_total * c;
+    for (int i = threadIdx.x; i < j_total * c; i += blockDim.x) s_w[i] = wout[i];
+    for (int i = threadIdx.x; i < j_total; i += blockDim.x) s_b[i] = bout ? bout[i] : 0.f;
+    __syncthreads();
+    const long long spatial = 1ll * t * h * w;
+    const long long total = 1ll * n * spatial;
+    const int quads = c / 4;
+    for (long long v = blockIdx.x * 1ll * blockDim.x + threadIdx.x; v < total; v += 1ll * gridDim.x * blockDim.x) {
+        long long r = v;
+        const int wo = static_cast<int>(r % w); r /= w;
+        const int ho = static_cast<int>(r % h); r /= h;
+        const int to = static_cast<int>(r % t);
+        const int nn = static_cast<int>(r / t);
+        const Tri tr = make_tri(nn, to, ho, wo, st, tl, hl, wl, c);
+        const float4* zrow = reinterpret_cast<const float4*>(z + static_cast<size_t>(v) * c);
+        for (int j0 = 0; j0 < j_total; j0 += kHeadJChunk) {
+            float acc[kHeadJChunk];
+#pragma unroll
+            for (int j = 0; j < kHeadJChunk; ++j) acc[j] = 0.f;
+            for (int q = 0; q < quads; ++q) {
+                const float4 zz = __ldg(zrow + q);
+                float xv[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (tr.wgt[k] != 0.f) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(ylow + tr.off[k]) + q);
+                        xv[0] = fmaf(tr.wgt[k], a.x, xv[0]);
+                        xv[1] = fmaf(tr.wgt[k], a.y, xv[1]);
+                        xv[2] = fmaf(tr.wgt[k], a.z, xv[2]);
+                        xv[3] = fmaf(tr.wgt[k], a.w, xv[3]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kHeadJChunk; ++j) {
+                    if (j0 + j < j_total) {
+                        const float* wr = s_w + (j0 + j) * c + 4 * q;
+                        acc[j] = fmaf(xv[0], wr[0], acc[j]);
+                        acc[j] = fmaf(xv[1], wr[1], acc[j]);
+                        acc[j] = fmaf(xv[2], wr[2], acc[j]);
+                        acc[j] = fmaf(xv[3], wr[3], acc[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kHeadJChunk; ++j) {
+                const int jj = j0 + j;
+                if (jj >= j_total) break;
+                float val = acc[j] + s_b[jj];
+                const int a = act[jj];
+                if (a == 1) val = tanhf(0.25f * val);
+                else if (a == 2) val = 1.0f / (1.0f + expf(-val));
+                const int cd = coord[jj];
+                if (cd == 1) val += linspace_value(t_abs, t, to);
+                else if (cd == 2) val += linspace_value(y_abs, h, ho);
+                else if (cd == 3) val += linspace_value(x_abs, w, wo);
+                out[(static_cast<size_t>(nn) * j_total + jj) * spatial + (v - static_cast<long long>(nn) * spatial)] = val;
+            }
+        }
+    }
+}
+
+inline unsigned grid_for(long long total, int block, int waves = 8) {
+    long long blocks = (total + block - 1) / block;
+    const long long cap = static_cast<long long>(device_sm_count()) * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<unsigned>(blocks);
+}
+
+}  // namespace
+}  // namespace stemseg
+
+using namespace stemseg;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int32_t stemseg_pack_activation(const float* src, int64_t stride_n, int64_t stride_c, int64_t stride_t,
+                                           int32_t n, int32_t c, int32_t t, int32_t hw, void* dst_planes,
+                                           int32_t planes, void* stream_) {
+    SS_REQUIRE(src && dst_planes, "pack_activation: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "pack_activation: planes must be 1 or 2");
+    SS_REQUIRE(n >= 1 && c >= 2 && c % 2 == 0 && t >= 1 && hw >= 1, "pack_activation: bad shape");
+    SS_REQUIRE(1ll * n * t <= 65535, "pack_activation: n*t too large");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t plane_elems = static_cast<size_t>(n) * t * hw * c;
+    dim3 grid((hw + kPackS - 1) / kPackS, (c + kPackC - 1) / kPackC, n * t);
+    pack_ncthw_kernel<<<grid, 256, 0, stream>>>(src, stride_n, stride_c, stride_t, c, t, hw,
+                                                static_cast<__nv_bfloat16*>(dst_planes), plane_elems, planes);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_pack_conv_weight(const float* src, int32_t cout, int32_t cin_total, int32_t cin_begin,
+                                            int32_t cin_count, int32_t taps, void* dst_planes, int32_t row_begin,
+                                            int32_t rows_total, int32_t planes, void* stream_) {
+    SS_REQUIRE(src && dst_planes, "pack_conv_weight: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight: planes must be 1 or 2");
+    SS_REQUIRE(cout >= 1 && cin_count >= 1 && cin_begin >= 0 && cin_begin + cin_count <= cin_total && taps >= 1 &&
+                   row_begin >= 0 && row_begin + cout <= rows_total,
+               "pack_conv_weight: bad shape");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t plane_elems = static_cast<size_t>(rows_total) * taps * cin_count;
+    const long long total = 1ll * cout * taps * cin_count;
+    pack_weight_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, cout, cin_total, cin_begin, cin_count, taps,
+                                                                 static_cast<__nv_bfloat16*>(dst_planes), row_begin,
+                                                                 plane_elems, planes);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c) {
+    const long long chunks = (spatial + kStatsChunk - 1) / kStatsChunk;
+    return align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
+}
+
+extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t n, int64_t spatial, int32_t c,
+                                            int32_t channels_per_group, float eps, float* mean_rstd,
+                                            void* workspace, size_t workspace_bytes, void* stream_) {
+    SS_REQUIRE(x && mean_rstd && workspace, "group_norm_stats: null pointer");
+    SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
+    SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "group_norm_stats: bad group size");
+    SS_REQUIRE(aligned16(x), "group_norm_stats: x must be 16-byte aligned");
+    const size_t need = stemseg_group_norm_workspace_bytes(n, spatial, c);
+    if (workspace_bytes < need) {
+        set_error("group_norm_stats: workspace %zu < %zu bytes", workspace_bytes, need);
+        return STEMSEG_ERR_WORKSPACE;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int chunks = static_cast<int>((spatial + kStatsChunk - 1) / kStatsChunk);
+    const int quads = c / 4;
+    const int rows = 256 / quads >= 1 ? 256 / quads : 1;
+    const int threads = quads * rows;
+    const size_t smem = static_cast<size_t>(rows) * c * 2 * sizeof(float);
+    SS_REQUIRE(threads <= 1024 && smem <= 48 * 1024, "group_norm_stats: channel count %d unsupported", c);
+    gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, static_cast<float*>(workspace),
+                                                                  chunks);
+    gn_finalize_kernel<<<dim3(c / channels_per_group, n), 128, 0, stream>>>(
+        static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, mean_rstd);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_norm_relu_pool(const float* x, const float* mean_rstd, const float* gamma,
+                                          const float* beta, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                                          int32_t channels_per_group, int32_t pool, void* dst_planes,
+                                          int32_t planes, void* stream_) {
+    SS_REQUIRE(x && dst_planes, "norm_relu_pool: null pointer");
+    SS_REQUIRE((mean_rstd == nullptr) == (gamma == nullptr) && (gamma == nullptr) == (beta == nullptr),
+               "norm_relu_pool: mean_rstd/gamma/beta must all be given or all be null");
+    SS_REQUIRE(planes == 1 || planes == 2, "norm_relu_pool: planes must be 1 or 2");
+    SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");
+    SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "norm_relu_pool: bad group size");
+    SS_REQUIRE(aligned16(x) && aligned16(dst_planes), "norm_relu_pool: pointers must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int t_out = pool ? (t - 1) / 2 + 1 : t;
+    const size_t plane_elems = static_cast<size_t>(n) * t_out * h * w * c;
+    const long long total = 1ll * n * t_out * h * w * (c / 4);
+    auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
+    if (pool)
+        gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, dst, plane_elems, planes);
+    else
+        gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, dst, plane_elems, planes);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_upsample_add(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h,
+                                        int32_t w, int32_t c, int32_t t_scale, void* dst_planes, int32_t planes,
+                                        void* stream_) {
+    SS_REQUIRE(z && y_low && dst_planes, "upsample_add: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "upsample_add: planes must be 1 or 2");
+    SS_REQUIRE(t_scale == 1 || t_scale == 2, "upsample_add: temporal scale must be 1 or 2");
+    SS_REQUIRE(n >= 1 && t >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && t % t_scale == 0 && c >= 4 &&
+                   c % 4 == 0,
+               "upsample_add: bad shape");
+    SS_REQUIRE(aligned16(z) && aligned16(y_low) && aligned16(dst_planes), "upsample_add: pointers must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t plane_elems = static_cast<size_t>(n) * t * h * w * c;
+    const long long total = 1ll * n * t * h * w * (c / 4);
+    upsample_add_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+        z, y_low, n, t, h, w, c, t_scale, t / t_scale, h / 2, w / 2, static_cast<__nv_bfloat16*>(dst_planes),
+        plane_elems, planes);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_head_output(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h,
+                                       int32_t w, int32_t c, int32_t t_scale, const float* out_weight,
+                                       const float* out_bias, const int32_t* activation, const int32_t* coordinate,
+                                       int32_t n_out, float time_scale, float* out, void* stream_) {
+    SS_REQUIRE(z && y_low && out_weight && activation && coordinate && out, "head_output: null pointer");
+    SS_REQUIRE(t_scale == 1 || t_scale == 2, "head_output: temporal scale must be 1 or 2");
+    SS_REQUIRE(n >= 1 && t >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && t % t_scale == 0 && c >= 4 &&
+                   c % 4 == 0 && c <= kHeadMaxC,
+               "head_output: bad shape");
+    SS_REQUIRE(n_out >= 1 && n_out <= 64, "head_output: n_out %d out of range [1,64]", n_out);
+    SS_REQUIRE(aligned16(z) && aligned16(y_low), "head_output: pointers must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t smem = (static_cast<size_t>(n_out) * c + n_out) * sizeof(float);
+    SS_CUDA_OK(cudaFuncSetAttribute(head_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    // embedding_utils.py:31-37: x in [-max(1, W/H), +], y in [-max(1, H/W), +], t in [-time_scale, +]
+    const float x_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(w) / static_cast<double>(h)));
+    const float y_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(h) / static_cast<double>(w)));
+    const long long total = 1ll * n * t * h * w;
+    head_out_kernel<<<grid_for(total, 128, 16), 128, smem, stream>>>(z, y_low, n, t, h, w, c, t_scale, t / t_scale,
+                                                                      h / 2, w / 2, out_weight, out_bias, activation,
+                                                                      coordinate, n_out, x_abs, y_abs, time_scale,
+                                                                      out);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}

@@ -1,0 +1,214 @@
+"""B200 drop-in decoder heads with the reference's constructor signatures, attributes and state_dict keys.
+
+Mirrors (same argument names / meaning / error behaviour, same ``state_dict`` keys and shapes so that
+``load_state_dict(strict=True)`` of reference checkpoints works, inference_model.py:27-28):
+  * ``EmbeddingHead``  <- SqueezingExpandDecoder  stemseg/modeling/embedding_decoder.py:11-145
+  * ``SeedinessHead``  <- SqueezingExpandDecoder  stemseg/modeling/seediness_decoder.py:11-112
+  * ``SemsegHead``     <- SqueezeExpandDecoder    stemseg/modeling/semseg_decoder.py:12-116
+The ``nn.Conv3d`` / ``nn.GroupNorm`` sub-modules below are *parameter containers only* (they are never called):
+``forward`` repacks their weights into kernel layout once and runs the CUDA plan of stemseg_b200/decoder.py.
+There is no PyTorch fallback: non-CUDA inputs raise.
+"""
+import torch
+import torch.nn as nn
+
+from stemseg_b200 import decoder as D
+from stemseg_b200.registry import EMBEDDING_HEAD_REGISTRY, SEEDINESS_HEAD_REGISTRY, SEMSEG_HEAD_REGISTRY
+
+# stemseg/modeling/embedding_utils.py:4-26
+_EMBEDDING_DIMS = {"xy": 2, "ff": 2, "xyt": 3, "xyf": 3, "xytf": 4, "xyff": 4, "xytff": 5, "xyfff": 5}
+_FREE_DIMS = {"xyf": 1, "xytf": 1, "xyff": 2, "xytff": 2, "xyfff": 3}
+# coordinate added to each leading embedding channel (embedding_utils.py:44-120)
+_OFFSETS = {"xy": "yx", "ff": "", "xyt": "tyx", "xyf": "yx", "xytf": "tyx", "xyff": "yx", "xytff": "tyx",
+            "xyfff": "yx"}
+_COORD_CODE = {"t": D.COORD_T, "y": D.COORD_Y, "x": D.COORD_X}
+
+
+def get_nb_embedding_dims(mode):
+    if mode not in _EMBEDDING_DIMS:
+        raise ValueError("Invalid experimental embedding mode: {}".format(mode))
+    return _EMBEDDING_DIMS[mode]
+
+
+def get_nb_free_dims(mode):
+    return _FREE_DIMS.get(mode, 0)
+
+
+def _resolve_num_frames(num_frames):
+    """The reference reads cfg.INPUT.NUM_FRAMES at construction (stemseg/modeling/common.py:15,28)."""
+    if num_frames is not None:
+        return int(num_frames)
+    try:
+        from stemseg.config import cfg
+    except ImportError:
+        raise ValueError("num_frames must be given when the reference's stemseg.config is not importable")
+    return int(cfg.INPUT.NUM_FRAMES)
+
+
+class _SqueezeExpandTrunk(nn.Module):
+    """Parameter layout of the shared trunk (embedding_decoder.py:20-80) + the CUDA forward."""
+
+    def __init__(self, in_channels, inter_channels, PoolType, NormType, num_frames, precision):
+        super().__init__()
+        if PoolType is not nn.AvgPool3d:
+            raise NotImplementedError("only PoolType=nn.AvgPool3d (cfg POOL_TYPE 'avg') has a CUDA path")
+        if precision not in D.PRECISION_PLANES:
+            raise ValueError("precision must be 'fp32' (bf16x2 split, 1e-4 parity) or 'bf16'")
+        self.num_frames = _resolve_num_frames(num_frames)
+        self._pools, self._tscale = D.pool_schedule(self.num_frames)
+        self.precision = precision
+        self.in_channels = in_channels
+        self.inter_channels = list(inter_channels)
+
+        def stage(cin, cout, slot, pooled_block=True):
+            pool = nn.AvgPool3d(3, stride=(2, 1, 1), padding=1) if (pooled_block and self._pools[slot]) else nn.Identity()
+            mods = [nn.Conv3d(cin, cout, 3, stride=1, padding=1), NormType(cout), nn.ReLU(inplace=True)]
+            return mods + ([pool] if pooled_block else [])
+
+        c = self.inter_channels
+        self.block_32x = nn.Sequential(*(stage(in_channels, c[0], 0) + stage(c[0], c[0], 1) + stage(c[0], c[0], 2)))
+        self.block_16x = nn.Sequential(*(stage(in_channels, c[1], 0) + stage(c[1], c[1], 1)))
+        self.block_8x = nn.Sequential(*stage(in_channels, c[2], 0))
+        self.block_4x = nn.Sequential(*stage(in_channels, c[3], 0, pooled_block=False))
+        self.conv_16 = nn.Conv3d(c[0] + c[1], c[1], 1, bias=False)
+        self.conv_8 = nn.Conv3d(c[1] + c[2], c[2], 1, bias=False)
+        self.conv_4 = nn.Conv3d(c[2] + c[3], c[3], 1, bias=False)
+
+        norm = self.block_32x[1]
+        if isinstance(norm, nn.GroupNorm):
+            self._num_groups, self._eps, self._has_norm = norm.num_groups, norm.eps, True
+        elif isinstance(norm, nn.Identity):
+            self._num_groups, self._eps, self._has_norm = 1, 0.0, False
+        else:
+            raise NotImplementedError("NormType %r has no CUDA path (GroupNorm or Identity only)" % (type(norm),))
+        for ch in [in_channels] + self.inter_channels:
+            if ch % 32 != 0:
+                raise ValueError("channel counts must be multiples of 32 (got %d)" % ch)
+        self._packed = None
+        self._packed_key = None
+
+    # ---- weight repacking (lazy, invalidated when a parameter is modified or moved) ------------------------
+    def _trunk_state(self):
+        return {k: v for k, v in self.named_parameters()}
+
+    def _cache_key(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters()) + (self.precision,)
+
+    def _output_spec(self, state):
+        raise NotImplementedError
+
+    def _get_packed(self):
+        key = self._cache_key()
+        if self._packed is None or self._packed_key != key:
+            state = self._trunk_state()
+            planes = D.PRECISION_PLANES[self.precision]
+            weights = D.TrunkWeights(state, self.inter_channels, planes, self._has_norm)
+            self._packed = (weights, self._output_spec(state))
+            self._packed_key = key
+        return self._packed
+
+    def _run(self, feats_32_16_8_4, trace=None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
+                any(f.requires_grad for f in feats_32_16_8_4):
+            raise NotImplementedError("the CUDA decoder is inference-only in this round (backward kernels are a "
+                                      "'next' row, SURVEY.md §8f); call it under torch.no_grad()")
+        with torch.no_grad():
+            weights, spec = self._get_packed()
+            return D.run_trunk_and_outputs(weights, feats_32_16_8_4, self.num_frames, self._num_groups, self._eps,
+                                           D.PRECISION_PLANES[self.precision], spec, trace=trace)
+
+
+@EMBEDDING_HEAD_REGISTRY.add("squeeze_expand_decoder")
+class EmbeddingHead(_SqueezeExpandTrunk):
+    """embedding_decoder.py:12-145: output cat(embeddings, variances[, seediness]) [N, E+V+S, T, H/4, W/4]."""
+
+    def __init__(self, in_channels, inter_channels, embedding_size, tanh_activation, seediness_output,
+                 experimental_dims, ConvType=nn.Conv3d, PoolType=nn.AvgPool3d, NormType=nn.Identity,
+                 num_frames=None, precision="fp32"):
+        if ConvType is not nn.Conv3d:
+            raise NotImplementedError("only ConvType=nn.Conv3d has a CUDA path")
+        super().__init__(in_channels, inter_channels, PoolType, NormType, num_frames, precision)
+        self.embedding_size = embedding_size
+        n_free_dims = get_nb_free_dims(experimental_dims)
+        self.variance_channels = self.embedding_size - n_free_dims
+        self.embedding_dim_mode = experimental_dims
+        embedding_output_size = get_nb_embedding_dims(self.embedding_dim_mode)
+        c3 = self.inter_channels[-1]
+        self.conv_embedding = nn.Conv3d(c3, embedding_output_size, kernel_size=1, padding=0, bias=False)
+        self.conv_variance = nn.Conv3d(c3, self.variance_channels, kernel_size=1, padding=0, bias=True)
+        self.conv_seediness, self.seediness_channels = None, 0
+        if seediness_output:
+            self.conv_seediness = nn.Conv3d(c3, 1, kernel_size=1, padding=0, bias=False)
+            self.seediness_channels = 1
+        self.tanh_activation = tanh_activation
+        self.register_buffer("time_scale", torch.tensor(1.0, dtype=torch.float32))
+
+    def _cache_key(self):
+        return super()._cache_key() + (float(self.time_scale),)
+
+    def _output_spec(self, state):
+        e_out = self.conv_embedding.weight.shape[0]
+        c3 = self.inter_channels[-1]
+        ws = [self.conv_embedding.weight.reshape(e_out, c3), self.conv_variance.weight.reshape(-1, c3)]
+        bias = [torch.zeros(e_out, device=ws[0].device), self.conv_variance.bias]
+        act = [D.ACT_TANH_QUARTER if self.tanh_activation else D.ACT_IDENTITY] * e_out + \
+              [D.ACT_IDENTITY] * self.variance_channels
+        offs = _OFFSETS[self.embedding_dim_mode]
+        coord = [_COORD_CODE[offs[i]] if i < len(offs) else D.COORD_NONE for i in range(e_out)] + \
+                [D.COORD_NONE] * self.variance_channels
+        if self.conv_seediness is not None:
+            ws.append(self.conv_seediness.weight.reshape(1, c3))
+            bias.append(torch.zeros(1, device=ws[0].device))
+            act.append(D.ACT_SIGMOID)
+            coord.append(D.COORD_NONE)
+        return D.OutputSpec(torch.cat([w.detach() for w in ws], 0), torch.cat([b.detach() for b in bias], 0), act,
+                            coord, float(self.time_scale))
+
+    def forward(self, x, trace=None):
+        """x: list of 4 feature maps [N, C, T, H, W] in increasing spatial size (strides 32, 16, 8, 4)."""
+        assert len(x) == 4, "Expected 4 feature maps, got {}".format(len(x))
+        return self._run(list(x), trace=trace)
+
+
+@SEEDINESS_HEAD_REGISTRY.add("squeeze_expand_decoder")
+class SeedinessHead(_SqueezeExpandTrunk):
+    """seediness_decoder.py:12-112: sigmoid(conv_out(trunk)) [N, 1, T, H/4, W/4]."""
+
+    def __init__(self, in_channels, inter_channels, ConvType=nn.Conv3d, PoolType=nn.AvgPool3d,
+                 NormType=nn.Identity, num_frames=None, precision="fp32"):
+        if ConvType is not nn.Conv3d:
+            raise NotImplementedError("only ConvType=nn.Conv3d has a CUDA path")
+        super().__init__(in_channels, inter_channels, PoolType, NormType, num_frames, precision)
+        self.conv_out = nn.Conv3d(self.inter_channels[3], 1, kernel_size=1, padding=0, bias=False)
+
+    def _output_spec(self, state):
+        return D.OutputSpec(self.conv_out.weight.reshape(1, -1), None, [D.ACT_SIGMOID], [D.COORD_NONE])
+
+    def forward(self, x, trace=None):
+        assert len(x) == 4
+        return self._run(list(x), trace=trace)
+
+
+@SEMSEG_HEAD_REGISTRY.add("squeeze_expand_decoder")
+class SemsegHead(_SqueezeExpandTrunk):
+    """semseg_decoder.py:13-116: logits [N, num_classes(+1), T, H/4, W/4]; input list is highest resolution first."""
+
+    def __init__(self, in_channels, num_classes, inter_channels, feature_scales, foreground_channel=False,
+                 ConvType=nn.Conv3d, PoolType=nn.AvgPool3d, NormType=nn.Identity, num_frames=None,
+                 precision="fp32"):
+        if ConvType is not nn.Conv3d:
+            raise NotImplementedError("only ConvType=nn.Conv3d has a CUDA path")
+        super().__init__(in_channels, inter_channels, PoolType, NormType, num_frames, precision)
+        self.is_3d = True
+        assert tuple(feature_scales) == (4, 8, 16, 32)
+        out_channels = num_classes + 1 if foreground_channel else num_classes
+        self.conv_out = nn.Conv3d(self.inter_channels[3], out_channels, kernel_size=1, padding=0, bias=False)
+        self.has_foreground_channel = foreground_channel
+
+    def _output_spec(self, state):
+        j = self.conv_out.weight.shape[0]
+        return D.OutputSpec(self.conv_out.weight.reshape(j, -1), None, [D.ACT_IDENTITY] * j, [D.COORD_NONE] * j)
+
+    def forward(self, x, trace=None):
+        assert len(x) == 4, "Expected 4 feature maps, got {}".format(len(x))
+        return self._run(list(x)[::-1], trace=trace)            # semseg_decoder.py:94

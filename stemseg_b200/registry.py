@@ -1,0 +1,81 @@
+"""Plugin tables with the reference's ``GlobalRegistry`` interface (stemseg/utils/global_registry.py:1-74).
+
+The reference selects its heads by name through three registries ("EmbeddingHead", "SeedinessHead", "SemsegHead",
+model_builder.py:282,309,325).  ``install_into_reference()`` puts the B200 heads into those tables -- under the
+reference's own key ``squeeze_expand_decoder`` (replacing the torch implementation, so unmodified YAML configs and
+``build_model()`` pick the CUDA heads) and under ``squeeze_expand_decoder_b200``.
+"""
+
+
+class GlobalRegistry(object):
+    _REGISTRIES = dict()
+
+    def __init__(self, name):
+        self._name = name
+        self._obj_map = dict()
+
+    def __getitem__(self, name):
+        if name not in self._obj_map:
+            raise KeyError("No object with name '{}' is registered under '{}'".format(name, self._name))
+        return self._obj_map[name]
+
+    def __contains__(self, name):
+        return name in self._obj_map
+
+    @staticmethod
+    def exists(name):
+        return name in GlobalRegistry._REGISTRIES
+
+    @staticmethod
+    def get(name):
+        if name not in GlobalRegistry._REGISTRIES:
+            GlobalRegistry._REGISTRIES[name] = GlobalRegistry(name)
+        return GlobalRegistry._REGISTRIES[name]
+
+    @staticmethod
+    def register(registry_name, obj_name=None, obj=None):
+        return GlobalRegistry.get(registry_name).add(obj_name, obj)
+
+    def _do_register(self, name, obj):
+        assert (name not in self._obj_map), \
+            "An object named '{}' was already registered in '{}' registry!".format(name, self._name)
+        self._obj_map[name] = obj
+
+    def add(self, name=None, obj=None):
+        if obj is None:
+            def deco(func_or_class):
+                self._do_register(name if name is not None else func_or_class.__name__, func_or_class)
+                return func_or_class
+            return deco
+        self._do_register(name if name else obj.__name__, obj)
+        return None
+
+
+EMBEDDING_HEAD_REGISTRY = GlobalRegistry.get("EmbeddingHead")
+SEEDINESS_HEAD_REGISTRY = GlobalRegistry.get("SeedinessHead")
+SEMSEG_HEAD_REGISTRY = GlobalRegistry.get("SemsegHead")
+
+B200_KEY = "squeeze_expand_decoder_b200"
+
+
+def install_into_reference(replace_default=True):
+    """Register the B200 heads and clusterer inside an importable reference tree (``import stemseg``)."""
+    from stemseg.utils.global_registry import GlobalRegistry as RefRegistry
+    import stemseg.modeling.embedding_decoder  # noqa: F401  (fills the reference tables first)
+    import stemseg.modeling.seediness_decoder  # noqa: F401
+    import stemseg.modeling.semseg_decoder  # noqa: F401
+    from stemseg_b200 import heads
+    for table, cls in (("EmbeddingHead", heads.EmbeddingHead), ("SeedinessHead", heads.SeedinessHead),
+                       ("SemsegHead", heads.SemsegHead)):
+        reg = RefRegistry.get(table)
+        reg._obj_map[B200_KEY] = cls
+        if replace_default:
+            reg._obj_map["squeeze_expand_decoder"] = cls
+    import stemseg.inference.clusterers as ref_clusterers
+    from stemseg_b200.clusterers import SequentialClustering
+    ref_clusterers.SequentialClustering = SequentialClustering
+    try:
+        import stemseg.inference.main as ref_main
+        ref_main.SequentialClustering = SequentialClustering
+    except Exception:        # the CLI module needs dataset dependencies that may be absent
+        pass

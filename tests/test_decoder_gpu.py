@@ -1,0 +1,159 @@
+"""GPU parity of the CUDA decoder heads (through the C ABI) vs the torch-fp32 oracle and the reference goldens.
+
+Tolerance (BASELINE north_star): fp32 outputs within 1e-4 *norm-wise per output group*
+(max|a-b| <= 1e-4 * max|ref| over the embedding / variance / seediness / logit channels; element-wise relative
+error is meaningless because outputs cross zero -- SURVEY.md §7).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import decoder_cases as dc
+from oracle import decoder_oracle as do
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+
+
+def build_head(case, sd, device, precision="fp32"):
+    from functools import partial
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    norm = partial(nn.GroupNorm, 32)
+    if case["kind"] == "embedding":
+        head = heads.EmbeddingHead(case["in_channels"], case["inter"], case["embedding_size"],
+                                   tanh_activation=case["tanh"], seediness_output=case["seediness_output"],
+                                   experimental_dims=case["dim_mode"], PoolType=nn.AvgPool3d, NormType=norm,
+                                   num_frames=case["num_frames"], precision=precision)
+    elif case["kind"] == "seediness":
+        head = heads.SeedinessHead(case["in_channels"], case["inter"], PoolType=nn.AvgPool3d, NormType=norm,
+                                   num_frames=case["num_frames"], precision=precision)
+    else:
+        head = heads.SemsegHead(case["in_channels"], case["num_out"] - 1, inter_channels=case["inter"],
+                                feature_scales=[4, 8, 16, 32], foreground_channel=True, PoolType=nn.AvgPool3d,
+                                NormType=norm, num_frames=case["num_frames"], precision=precision)
+    head.load_state_dict(sd, strict=True)        # identical keys / shapes to the reference heads
+    return head.to(device).eval()
+
+
+def output_groups(case, n_channels):
+    if case["kind"] != "embedding":
+        return {"all": slice(0, n_channels)}
+    e = do.EMBEDDING_DIMS[case["dim_mode"]]
+    v = case["embedding_size"] - do.FREE_DIMS.get(case["dim_mode"], 0)
+    g = {"embedding": slice(0, e), "variance": slice(e, e + v)}
+    if case["seediness_output"]:
+        g["seediness"] = slice(e + v, e + v + 1)
+    return g
+
+
+def assert_close(got, ref, case, tol):
+    assert got.shape == ref.shape
+    for name, sl in output_groups(case, ref.shape[1]).items():
+        a, b = got[:, sl].double(), ref[:, sl].double()
+        err = (a - b).abs().max().item() / b.abs().max().item()
+        assert err <= tol, "%s: norm-wise error %.3e > %.1e" % (name, err, tol)
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "decoder_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(dc.case_table().keys()))
+def test_head_matches_reference_golden(name, golden, cuda_device):
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    with torch.no_grad():
+        out = head([f.to(cuda_device) for f in feats])
+    assert out.device.type == "cuda" and out.dtype == torch.float32
+    assert_close(out.cpu(), torch.from_numpy(golden[name]), case, FP32_TOL)
+
+
+def test_layerwise_bisect(cuda_device):
+    """Per-layer check (conv outputs of every stage) so that a mismatch localises."""
+    name = "emb_xyff_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    trace_ref, trace = {}, {}
+    dc.run_oracle(name, trace=trace_ref)
+    with torch.no_grad():
+        head([f.to(cuda_device) for f in feats], trace=trace)
+    assert trace
+    for key, y in trace.items():
+        ref = trace_ref[key]                                   # [N,C,T,H,W]
+        got = y.permute(0, 4, 1, 2, 3).cpu()                   # NDHWC -> NCDHW
+        err = (got.double() - ref.double()).abs().max().item() / ref.abs().max().item()
+        assert err <= 2e-5, "%s: %.3e" % (key, err)
+
+
+def test_bf16_mode(cuda_device):
+    """bf16 operands cannot meet 1e-4 by construction: own tolerance, 2e-2 norm-wise."""
+    name = "emb_fullwidth_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device, precision="bf16")
+    with torch.no_grad():
+        out = head([f.to(cuda_device) for f in feats])
+    ref = dc.run_oracle(name)
+    assert_close(out.cpu(), ref, case, 2e-2)
+
+
+def test_permuted_input_views(cuda_device):
+    """Training-style inputs: [N*T,C,H,W] viewed and permuted to NCTHW without a copy (model_builder.py:84-99)."""
+    name = "emb_xyff_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    views = []
+    for f in feats:
+        n, c, t, h, w = f.shape
+        flat = f.permute(0, 2, 1, 3, 4).reshape(n * t, c, h, w).contiguous().to(cuda_device)
+        views.append(flat.view(n, t, c, h, w).permute(0, 2, 1, 3, 4))
+        assert not views[-1].is_contiguous()
+    with torch.no_grad():
+        out = head(views)
+        out2 = head([f.to(cuda_device) for f in feats])
+    assert torch.equal(out, out2)
+
+
+def test_deterministic_and_cached_weights(cuda_device):
+    name = "seediness_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    dev_feats = [f.to(cuda_device) for f in feats]
+    with torch.no_grad():
+        a = head(dev_feats)
+        b = head(dev_feats)
+        assert torch.equal(a, b)
+        head.conv_out.weight.mul_(2.0)               # parameter update invalidates the packed copy
+        c = head(dev_feats)
+    assert not torch.equal(a, c)
+
+
+def test_rejects_cpu_inputs():
+    sd, feats, case = dc.build_case("seediness_t8")
+    from functools import partial
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    head = heads.SeedinessHead(case["in_channels"], case["inter"], NormType=partial(nn.GroupNorm, 32), num_frames=8)
+    with pytest.raises((ValueError, ImportError)):
+        head(feats)
+
+
+@pytest.mark.parametrize("t,h4,w4", [(8, 120, 216)])
+def test_full_size_480p_vs_oracle(t, h4, w4, cuda_device):
+    """BASELINE config 2: 8x480x864 clip, real channel widths, fp32 parity against the CPU oracle."""
+    case = dict(kind="embedding", in_channels=256, inter=[256, 256, 128, 128], num_frames=t, n=1, h4=h4, w4=w4,
+                embedding_size=4, dim_mode="xyff", tanh=True, seediness_output=True)
+    shapes = do.head_parameter_shapes("embedding", 256, case["inter"], embedding_size=4, dim_mode="xyff",
+                                      seediness_output=True)
+    sd = do.seeded_state_dict(shapes, 4242)
+    feats = do.seeded_features(4243, 1, 256, t, h4, w4)
+    torch.set_num_threads(min(64, os.cpu_count() or 8))
+    ref = do.embedding_head(sd, feats, t, 4, "xyff", True, True)
+    head = build_head(case, sd, cuda_device)
+    with torch.no_grad():
+        out = head([f.to(cuda_device) for f in feats])
+    assert_close(out.cpu(), ref, case, FP32_TOL)
