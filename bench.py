@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the STEm-Seg hot path on B200: decoder heads + foreground gather + sequential clustering.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|bf16]
+
+A *step* is one pass of the hot path over one synthetic 8x480x854 clip (padded to 480x864 like
+structures/image_list.py:93-95): FPN pyramid [1,256,8,{15x27,30x54,60x108,120x216}] fp32 -> embedding head +
+seediness head (DAVIS config, davis_1.yaml) -> foreground compaction/gather (all voxels foreground, bandwidth
+activation fused) -> SequentialClustering(0.5, 0.3, min_seediness_prob=0.0) over the 207 360 embedding-grid points ->
+int64 labels.  BASELINE.json configs[1].  With N > 1 every rank processes its own clips (weak scaling: the path
+shards at sub-clip granularity with no data-path collective).
+
+`value` times K steps with the pyramid resident in HBM (CUDA events, max over ranks).  `e2e` times the same call with
+the pyramid in pinned host memory: H2D of the 282 MB pyramid and D2H of the labels inside the timed region.
+`--impl reference` times the reference's CPU path (oracle port: the same torch-CPU ATen kernels the reference's
+modules call, all host threads) on the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T, H, W = 8, 480, 854
+HP, WP = 480, 864                      # padded to multiples of 32
+H4, W4 = HP // 4, WP // 4
+IN_CH = 256
+INTER = (256, 256, 128, 128)
+GRID_POINTS = T * H4 * W4              # 207 360
+VOXELS_PER_CLIP = T * H * W            # 3 279 360 input-resolution voxels
+WORKLOAD = "8x480x854 clip (pad 480x864): DAVIS heads (embedding+seediness, [256,256,128,128]) + fg gather + " \
+           "SequentialClustering over 207360 points"
+
+
+def make_features_cpu(seed=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    feats = {}
+    for s in (32, 16, 8, 4):
+        feats[s] = torch.randn(1, IN_CH, T, HP // s, WP // s, generator=g, dtype=torch.float32)
+    return feats
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------------------------------
+def build_cpu_reference(seed=42):
+    import torch
+    from oracle import decoder_oracle as do
+    emb_shapes = do.head_parameter_shapes("embedding", IN_CH, list(INTER), embedding_size=4, dim_mode="xyff",
+                                          seediness_output=False)
+    seed_shapes = do.head_parameter_shapes("seediness", IN_CH, list(INTER))
+    return do.seeded_state_dict(emb_shapes, seed), do.seeded_state_dict(seed_shapes, seed + 1)
+
+
+def cpu_reference_step(feats, emb_sd, seed_sd):
+    """One clip through the oracle (torch CPU fp32 heads + numpy gather + numpy clustering)."""
+    import numpy as np
+    import torch
+    from oracle import cluster_oracle as co
+    from oracle import decoder_oracle as do
+    from oracle import gather_oracle as go
+    with torch.no_grad():
+        f = [feats[s] for s in (32, 16, 8, 4)]
+        out = do.embedding_head(emb_sd, f, T, 4, "xyff", True, False)[0]
+        seediness = do.seediness_head(seed_sd, f, T)[0]
+        emb, var = out[:4], out[4:6]
+        bw = var.exp() * 10.0
+    mask = np.ones((T, H4, W4), dtype=bool)
+    coords, _ = go.masks_to_coord_list(mask)
+    e, b, s = go.gather_foreground(coords, emb.numpy(), bw.numpy(), seediness.numpy())
+    labels, meta = co.sequential_cluster(e, b, s, 0.5, 0.3, 0.0, 2, [0.3, 0.3])
+    return labels, meta
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    feats = make_features_cpu()
+    emb_sd, seed_sd = build_cpu_reference()
+    for _ in range(args.warmup):
+        cpu_reference_step(feats, emb_sd, seed_sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(feats, emb_sd, seed_sd)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "timing": "host wall clock"},
+        "mvoxels_per_sec": value * VOXELS_PER_CLIP / 1e6,
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": "%d full clips (oracle port of the reference's torch-CPU heads + clustering)" % args.steps},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--id=%d" % self.gpu_index, "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for row in open(self.path):
+                parts = [p.strip() for p in row.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                    "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def run_gpu_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from stemseg_b200 import _lib, decoder
+    from stemseg_b200.pipeline import build_davis_pipeline
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    lib = _lib.load()                         # raises if the CUDA library is missing: no fallback
+    _lib.check(lib.stemseg_check_device())
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+
+    pipe = build_davis_pipeline(device, num_frames=T, precision=args.precision)
+    host_feats = {s: f.pin_memory() for s, f in make_features_cpu(seed=rank).items()}
+    dev_feats = {s: f.to(device, non_blocking=True) for s, f in host_feats.items()}
+    fg_mask = torch.ones((T, H4, W4), dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        return pipe(dev_feats, fg_mask=fg_mask)
+
+    def step_e2e():
+        feats = {s: f.to(device, non_blocking=True) for s, f in host_feats.items()}
+        res = pipe(feats, fg_mask=fg_mask)
+        return res.labels.cpu()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if profile:
+            decoder.PROFILE_EVENTS = []
+        start.record()
+        for _ in range(steps):
+            fn()
+        end.record()
+        barrier()
+        ms = start.elapsed_time(end)
+        events = None
+        if profile:
+            events, decoder.PROFILE_EVENTS = decoder.PROFILE_EVENTS, None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, events
+
+    for _ in range(args.warmup):
+        step_resident()
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.KERNEL_LAUNCHES[0] = 0
+    ms_total, conv_events = timed(step_resident, args.steps, profile=True)
+    launches = _lib.KERNEL_LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # per-stage breakdown (untimed extra pass on rank 0; informational)
+    stages = {}
+    if rank == 0:
+        def ev_time(fn, reps=3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, out
+        stages["heads_ms"], (emb, var, seedi, _) = ev_time(lambda: pipe.run_heads(dev_feats))
+        stages["gather_cluster_ms"], _ = ev_time(lambda: pipe.cluster(emb, var, seedi, fg_mask))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    clips = args.steps * world
+    value = clips / (ms_total * 1e-3)
+    e2e_value = clips / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel: the tcgen05 conv launch with the largest share of the step
+    by_shape = {}
+    for shape, a, b in conv_events:
+        by_shape.setdefault(shape, []).append(a.elapsed_time(b))
+    dom_shape, dom_times = max(by_shape.items(), key=lambda kv: sum(kv[1]))
+    n, t, h, w, cin, cout, ks, planes = dom_shape
+    flops = 2.0 * n * t * h * w * (27 if ks == 3 else 1) * cin * cout
+    dom_ms = sum(dom_times) / len(dom_times)
+    achieved = flops / (dom_ms * 1e-3) / 1e12
+    conv_ms_per_step = sum(sum(v) for v in by_shape.values()) / args.steps
+    planes_products = 3 if planes == 2 else 1
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+        "kernel": "conv_tc_kernel %dx%dx%dx%d cin=%d cout=%d k=%d planes=%d" % (n * t, h, w, 1, cin, cout, ks, planes),
+        "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
+        "algorithmic_gflop_per_launch": flops / 1e9,
+        "launch_ms": dom_ms,
+        "tensor_pipe_products_per_mac": planes_products,
+        "tensor_pipe_frac": achieved * planes_products / peaks["bf16_tflops_sustained"],
+        "share_of_step": sum(dom_times) / args.steps / (ms_total / args.steps),
+        "all_conv_share_of_step": conv_ms_per_step / (ms_total / args.steps),
+    }
+
+    # CPU baseline on a bounded sample (rank 0, N == 1 only)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        cfeats = make_features_cpu()
+        emb_sd, seed_sd = build_cpu_reference()
+        cpu_reference_step(cfeats, emb_sd, seed_sd)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 20):
+            cpu_reference_step(cfeats, emb_sd, seed_sd)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": reps / dt, "unit": "clips/s", "cores": threads, "kind": "port",
+                        "sample": "%d full clips after 1 warm-up (oracle port: torch-CPU fp32 heads + numpy gather/"
+                                  "clustering, all host threads)" % reps}
+
+    h2d = sum(f.numel() * f.element_size() for f in host_feats.values())
+    d2h = GRID_POINTS * 8
+    line = {
+        "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "precision": args.precision,
+                   "arithmetic": "bf16x2-split operands (hi*hi+hi*lo+lo*hi on tcgen05), fp32 accumulate"
+                   if args.precision == "fp32" else "bf16 operands, fp32 accumulate",
+                   "l2": "inputs larger than L2 (282 MB pyramid per step vs 126 MB L2)", "clips_per_step_per_gpu": 1,
+                   "parallelism": "clip-parallel x%d (no data-path collective)" % world},
+        "mvoxels_per_sec": value * VOXELS_PER_CLIP / 1e6,
+        "grid_points_per_sec": value * GRID_POINTS,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "stages": stages,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
+                             "--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

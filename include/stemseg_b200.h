@@ -111,13 +111,19 @@ size_t stemseg_fg_compact_workspace_bytes(int64_t n_frames, int64_t frame_voxels
  */
 int32_t stemseg_fg_compact(const uint8_t* mask, int64_t n_frames, int64_t frame_voxels, int32_t* indices,
                            int32_t* frame_counts, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the foreground test `values > threshold` on an fp32 map [T][HW] fused in (seediness > 0.25,
+ * stemseg/inference/main.py:93-103; foreground probability > 0.5, main.py:142-144). */
+int32_t stemseg_fg_compact_threshold(const float* values, float threshold, int64_t n_frames, int64_t frame_voxels,
+                                     int32_t* indices, int32_t* frame_counts, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 /*
  * src       device float [C][T*HW] channel-first map, channel stride `channel_stride` elements
  * indices   device int32 [n]
+ * transform 0 = copy; 1 = exp(x) * 10, the bandwidth activation of inference_model.py:148 fused into the gather
  * dst       device float [n][C] out
  */
 int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, int32_t channels, const int32_t* indices,
-                          int64_t n, float* dst, void* stream);
+                          int64_t n, int32_t transform, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3-D decoder heads (SqueezingExpandDecoder x3)

@@ -45,7 +45,9 @@ PROTOTYPES = {
     "stemseg_prob_threshold_to_distance": (c_float, [c_double]),
     "stemseg_fg_compact_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "stemseg_fg_compact": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "stemseg_fg_compact_threshold": (c_int32, [c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                               c_size_t, c_void_p]),
+    "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "stemseg_pack_activation": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_int32, c_void_p]),
     "stemseg_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
@@ -69,6 +71,34 @@ class StemsegError(RuntimeError):
 
 
 _lib = None
+# number of CUDA kernels launched through this binding (each wrapper adds the kernels its C call enqueues);
+# bench.py reports it as `gpu_launches`
+KERNEL_LAUNCHES = [0]
+KERNELS_PER_CALL = {
+    "stemseg_seq_cluster": 1, "stemseg_fg_compact": 3, "stemseg_fg_compact_threshold": 3, "stemseg_fg_gather": 1,
+    "stemseg_pack_activation": 1, "stemseg_pack_conv_weight": 1, "stemseg_conv3d_bf16_planes": 1,
+    "stemseg_group_norm_stats": 2, "stemseg_norm_relu_pool": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
+}
+
+
+class _Counted(object):
+    """Callable wrapper around one C entry point that keeps KERNEL_LAUNCHES up to date."""
+
+    def __init__(self, fn, kernels):
+        self._fn, self._kernels = fn, kernels
+
+    def __call__(self, *args):
+        KERNEL_LAUNCHES[0] += self._kernels
+        return self._fn(*args)
+
+
+class _Library(object):
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in PROTOTYPES:
+            fn = getattr(cdll, name)
+            k = KERNELS_PER_CALL.get(name, 0)
+            setattr(self, name, _Counted(fn, k) if k else fn)
 
 
 def load():
@@ -88,8 +118,8 @@ def load():
     if lib.stemseg_abi_version() != ABI_VERSION:
         raise ImportError("stemseg_b200: ABI version mismatch (library %d, binding %d) -- rebuild" % (
             lib.stemseg_abi_version(), ABI_VERSION))
-    _lib = lib
-    return lib
+    _lib = _Library(lib)
+    return _lib
 
 
 def check(rc):

@@ -30,6 +30,9 @@ COORD_NONE, COORD_T, COORD_Y, COORD_X = 0, 1, 2, 3
 
 PRECISION_PLANES = {"fp32": 2, "bf16": 1}
 
+# bench.py sets this to a list to collect (shape, start_event, end_event) around every conv launch
+PROFILE_EVENTS = None
+
 
 def pool_schedule(num_frames):
     if num_frames not in POOL_SLOTS:
@@ -108,9 +111,17 @@ def conv3d(act, packed, max_ctas=0):
     shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes)
     with torch.cuda.device(act.tensor.device):
         out = torch.empty((act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32, device=act.tensor.device)
+        ev = None
+        if PROFILE_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _check(lib.stemseg_conv3d_bf16_planes(_lib.ptr(act.tensor), _lib.ptr(packed.planes_tensor),
                                               _lib.ptr(packed.bias), _lib.ptr(out), shape, max_ctas,
                                               _lib.stream_ptr()))
+        if ev is not None:
+            ev[1].record()
+            PROFILE_EVENTS.append(((act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size,
+                                    act.planes), ev[0], ev[1]))
     return out
 
 

@@ -51,14 +51,22 @@ class ForegroundIndex(object):
 
 
 @torch.no_grad()
-def compact_foreground(masks):
-    """masks: [T,H,W] tensor on a CUDA device, any integer/bool dtype (non-zero = foreground)."""
+def compact_foreground(masks, threshold=None):
+    """masks: [T,H,W] tensor on a CUDA device, any integer/bool dtype (non-zero = foreground).
+
+    With ``threshold`` given, ``masks`` is an fp32 map and foreground = ``masks > threshold`` evaluated inside the
+    compaction kernel (seediness > 0.25, stemseg/inference/main.py:93-103).
+    """
     if masks.dim() != 3:
         raise ValueError("expected a [T,H,W] mask, got shape %s" % (tuple(masks.shape),))
     if not masks.is_cuda:
         raise ValueError("compact_foreground needs a CUDA tensor; there is no CPU path")
     t, h, w = masks.shape
-    if masks.dtype == torch.bool:
+    if threshold is not None:
+        if masks.dtype != torch.float32:
+            raise ValueError("thresholded compaction needs an fp32 map")
+        m = masks.contiguous()
+    elif masks.dtype == torch.bool:
         m = masks.contiguous().view(torch.uint8)
     elif masks.dtype == torch.uint8:
         m = masks.contiguous()
@@ -72,16 +80,21 @@ def compact_foreground(masks):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
         indices = torch.empty(t * h * w, dtype=torch.int32, device=masks.device)
         counts = torch.empty(t + 1, dtype=torch.int32, device=masks.device)
-        _lib.check(lib.stemseg_fg_compact(_lib.ptr(m), t, h * w, _lib.ptr(indices), _lib.ptr(counts), _lib.ptr(ws),
-                                          ws_bytes, _lib.stream_ptr()))
+        if threshold is not None:
+            _lib.check(lib.stemseg_fg_compact_threshold(_lib.ptr(m), float(threshold), t, h * w, _lib.ptr(indices),
+                                                        _lib.ptr(counts), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        else:
+            _lib.check(lib.stemseg_fg_compact(_lib.ptr(m), t, h * w, _lib.ptr(indices), _lib.ptr(counts),
+                                              _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
         counts_host = counts.cpu().tolist()          # one sync (the reference syncs once per frame)
     return ForegroundIndex(indices[:counts_host[-1]], counts_host[:-1], (t, h, w))
 
 
 @torch.no_grad()
-def gather_points(channel_first_map, fg_index):
+def gather_points(channel_first_map, fg_index, transform="none"):
     """channel_first_map: [C,T,H,W] fp32 CUDA tensor -> [N,C] rows for the foreground voxels (online_chainer.py:265-281)."""
     x = channel_first_map
+    code = {"none": 0, "exp10": 1}[transform]        # exp10: bandwidths = exp(v) * 10 (inference_model.py:148)
     if x.dim() != 4 or tuple(x.shape[1:]) != fg_index.shape:
         raise ValueError("map shape %s does not match mask shape %s" % (tuple(x.shape), fg_index.shape))
     if x.dtype != torch.float32 or not x.is_cuda:
@@ -97,5 +110,5 @@ def gather_points(channel_first_map, fg_index):
     lib = _lib.load()
     with torch.cuda.device(x.device):
         _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c,
-                                         _lib.ptr(fg_index.indices), n, _lib.ptr(out), _lib.stream_ptr()))
+                                         _lib.ptr(fg_index.indices), n, code, _lib.ptr(out), _lib.stream_ptr()))
     return out

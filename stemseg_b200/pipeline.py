@@ -1,0 +1,108 @@
+"""The hot path for one sub-clip, end to end on the device:
+
+    FPN feature pyramid -> embedding / seediness (/ semseg) heads -> split -> foreground compaction + gather
+    (bandwidths = exp(var) * 10 fused into the gather) -> sequential clustering -> per-frame label vectors
+
+i.e. what ``InferenceModel.forward`` does after the backbone for one sub-clip (stemseg/modeling/inference_model.py:
+121-162) followed by ``OnlineChainer.cluster_subsequence`` (stemseg/inference/online_chainer.py:244-289), without
+the reference's device -> host -> device round trip of the head outputs (inference_model.py:162 ->
+online_chainer.py:174-176).  ``SubclipPipeline.__call__`` is the public call benchmarked by bench.py.
+"""
+import torch
+
+from stemseg_b200.foreground import compact_foreground, gather_points
+
+
+class SubclipResult(object):
+    __slots__ = ("labels", "frame_labels", "meta", "fg_index", "embeddings", "variances", "seediness", "semseg_logits")
+
+
+class SubclipPipeline(object):
+    def __init__(self, embedding_head, seediness_head, clusterer, semseg_head=None, seediness_fg_threshold=0.25,
+                 embedding_scales=(32, 16, 8, 4), semseg_scales=(4, 8, 16, 32)):
+        self.embedding_head = embedding_head
+        self.seediness_head = seediness_head
+        self.semseg_head = semseg_head
+        self.clusterer = clusterer
+        self.seediness_fg_threshold = seediness_fg_threshold
+        self.embedding_scales = tuple(embedding_scales)
+        self.semseg_scales = tuple(semseg_scales)
+        if seediness_head is None and embedding_head.seediness_channels == 0:
+            raise ValueError("no seediness source: give a seediness head or an embedding head with seediness_output")
+
+    @torch.no_grad()
+    def run_heads(self, features):
+        """features: dict {scale: [1,C,T,h,w]} -> (embeddings [E,T,h,w], variances [V,T,h,w], seediness [1,T,h,w],
+        semseg logits or None).  Slices of one output tensor, as in inference_model.py:140-146."""
+        emb_in = [features[s] for s in self.embedding_scales]
+        if emb_in[0].shape[0] != 1:
+            raise ValueError("SubclipPipeline processes one sub-clip at a time (batch dimension must be 1)")
+        out = self.embedding_head(emb_in).squeeze(0)
+        e, v = self.embedding_head.embedding_size, self.embedding_head.variance_channels
+        embeddings, variances = out[:e], out[e:e + v]
+        if self.embedding_head.seediness_channels:
+            seediness = out[e + v:e + v + 1]
+        else:
+            seediness = self.seediness_head(emb_in).squeeze(0)
+        semseg = None
+        if self.semseg_head is not None:
+            semseg = self.semseg_head([features[s] for s in self.semseg_scales]).squeeze(0)
+        return embeddings, variances, seediness, semseg
+
+    @torch.no_grad()
+    def cluster(self, embeddings, variances, seediness, fg_mask=None, cluster_label_start=1,
+                return_label_masks=False):
+        """fg_mask: [T,h,w] (non-zero = foreground) or None -> seediness > seediness_fg_threshold
+        (stemseg/inference/main.py:93-103 for a single sub-clip)."""
+        if fg_mask is None:
+            fg = compact_foreground(seediness[0], threshold=self.seediness_fg_threshold)
+        else:
+            fg = compact_foreground(fg_mask)
+        emb_flat = gather_points(embeddings, fg)
+        bw_flat = gather_points(variances, fg, transform="exp10")      # inference_model.py:148
+        seed_flat = gather_points(seediness, fg)
+        labels, meta = self.clusterer(emb_flat, bandwidths=bw_flat, seediness=seed_flat,
+                                      cluster_label_start=cluster_label_start,
+                                      return_label_masks=return_label_masks)
+        assert labels.numel() == emb_flat.shape[0]                     # online_chainer.py:286
+        return labels, meta, fg
+
+    @torch.no_grad()
+    def __call__(self, features, fg_mask=None, cluster_label_start=1):
+        res = SubclipResult()
+        res.embeddings, res.variances, res.seediness, res.semseg_logits = self.run_heads(features)
+        if fg_mask is None and res.semseg_logits is not None and self.semseg_head.has_foreground_channel:
+            # foreground channel is the last one (inference_model.py:212-225); prob > 0.5 <=> logit > 0
+            fg = compact_foreground(res.semseg_logits[-1], threshold=0.0)
+            fg_mask_index = fg
+            emb_flat = gather_points(res.embeddings, fg)
+            bw_flat = gather_points(res.variances, fg, transform="exp10")
+            seed_flat = gather_points(res.seediness, fg)
+            res.labels, res.meta = self.clusterer(emb_flat, bandwidths=bw_flat, seediness=seed_flat,
+                                                  cluster_label_start=cluster_label_start)
+            res.fg_index = fg_mask_index
+        else:
+            res.labels, res.meta, res.fg_index = self.cluster(res.embeddings, res.variances, res.seediness, fg_mask,
+                                                              cluster_label_start)
+        res.frame_labels = list(res.labels.split(res.fg_index.frame_counts, 0))   # online_chainer.py:289
+        return res
+
+
+def build_davis_pipeline(device, num_frames=8, precision="fp32", in_channels=256,
+                         inter_channels=(256, 256, 128, 128), min_seediness_prob=0.0, seed=42):
+    """Random-init model of the shipped DAVIS config (davis_1.yaml: E=4 'xyff', separate seediness head, GN32,
+    free_dim_stds [0.3, 0.3]; defaults.yaml:114-117 clustering thresholds) on `device`."""
+    from functools import partial
+    import torch.nn as nn
+    from stemseg_b200.clusterers import SequentialClustering
+    from stemseg_b200.heads import EmbeddingHead, SeedinessHead
+    torch.manual_seed(seed)                                  # model_builder.py:252
+    norm = partial(nn.GroupNorm, 32)
+    emb = EmbeddingHead(in_channels, list(inter_channels), 4, tanh_activation=True, seediness_output=False,
+                        experimental_dims="xyff", PoolType=nn.AvgPool3d, NormType=norm, num_frames=num_frames,
+                        precision=precision)
+    seedi = SeedinessHead(in_channels, list(inter_channels), PoolType=nn.AvgPool3d, NormType=norm,
+                          num_frames=num_frames, precision=precision)
+    emb, seedi = emb.to(device).eval(), seedi.to(device).eval()
+    clusterer = SequentialClustering(0.5, 0.3, min_seediness_prob, 2, [0.3, 0.3], device)
+    return SubclipPipeline(emb, seedi, clusterer)
