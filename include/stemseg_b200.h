@@ -153,7 +153,13 @@ typedef struct StemsegConvShape {
     int32_t cin, cout;       /* multiples of 32                                                                 */
     int32_t kernel_size;     /* 3 (3x3x3, embedding_decoder.py:21) or 1 (1x1x1 merge, embedding_decoder.py:68)  */
     int32_t planes;          /* 1 or 2                                                                          */
+    int32_t split_k;         /* 1, or 3 / 9 / 27 (kernel_size 3): number of tap slices computed by separate CTAs;
+                                out then holds split_k partial sums [split_k][n][t][h][w][cout] (bias in slice 0)
+                                which the GroupNorm kernels add in a fixed order                                  */
 } StemsegConvShape;
+
+/* Split that fills the SMs for a latency-bound (few-tile) layer on the current device; 1 for large layers. */
+int32_t stemseg_conv3d_auto_split(const StemsegConvShape* shape);
 
 /* out[n][t][h][w][cout] (fp32) = conv(act) + bias.  tcgen05 implicit GEMM, TMA im2col, fp32 accumulation in TMEM.
  * max_ctas > 0 caps the persistent grid (used to run independent branches concurrently on separate streams). */
@@ -161,14 +167,16 @@ int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_pl
                                    const StemsegConvShape* shape, int32_t max_ctas, void* stream);
 
 /* GroupNorm statistics of an NDHWC fp32 tensor: mean_rstd[n][c/channels_per_group][2] (biased variance, eps inside
- * the sqrt) -- nn.GroupNorm(32, C) (model_builder.py:34). Deterministic (fixed reduction order). */
+ * the sqrt) -- nn.GroupNorm(32, C) (model_builder.py:34). Deterministic (fixed reduction order).
+ * x may be `slices` split-K partial sums [slices][n][spatial][c] (see StemsegConvShape.split_k). */
 size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
-int32_t stemseg_group_norm_stats(const float* x, int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
-                                 float eps, float* mean_rstd, void* workspace, size_t workspace_bytes, void* stream);
+int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int32_t n, int64_t spatial, int32_t c,
+                                 int32_t channels_per_group, float eps, float* mean_rstd, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* relu(group_norm(x)) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
  * (embedding_decoder.py:22-24; common.py:8-24).  mean_rstd/gamma/beta all NULL = no normalisation. */
-int32_t stemseg_norm_relu_pool(const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+int32_t stemseg_norm_relu_pool(const float* x, int32_t slices, const float* mean_rstd, const float* gamma, const float* beta,
                                int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t channels_per_group,
                                int32_t pool, void* dst_planes, int32_t planes, void* stream);
 

@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -29,7 +29,7 @@ class StemsegClusterParams(ctypes.Structure):
 
 class StemsegConvShape(ctypes.Structure):
     _fields_ = [("n", c_int32), ("t", c_int32), ("h", c_int32), ("w", c_int32), ("cin", c_int32), ("cout", c_int32),
-                ("kernel_size", c_int32), ("planes", c_int32)]
+                ("kernel_size", c_int32), ("planes", c_int32), ("split_k", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/stemseg_b200.h declares (tests check the two agree)
@@ -54,11 +54,12 @@ PROTOTYPES = {
                                            c_int32, c_int32, c_void_p]),
     "stemseg_conv3d_bf16_planes": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p,
                                              ctypes.POINTER(StemsegConvShape), c_int32, c_void_p]),
+    "stemseg_conv3d_auto_split": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
-    "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p,
-                                           c_size_t, c_void_p]),
-    "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
-                                         c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_float, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
+    "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "stemseg_upsample_add": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p, c_int32, c_void_p]),
     "stemseg_head_output": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,

@@ -36,8 +36,11 @@ struct ConvTcParams {
     int tt, th, tw;            // voxel box of one M tile (tt*th*tw == 128)
     int tiles_t, tiles_h, tiles_w;
     int n_tiles_n;
-    int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n
-    float* out;                // [n][t][h][w][cout] fp32
+    int k_slices;              // split-K over the taps: slice s handles taps [s*taps_per_slice, (s+1)*taps_per_slice)
+    int taps_per_slice;
+    size_t slice_stride;       // elements between the partial outputs of consecutive slices
+    int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n * k_slices
+    float* out;                // [k_slices][n][t][h][w][cout] fp32 (partial sums when k_slices > 1)
     const float* bias;         // [cout] or nullptr
 };
 
@@ -166,10 +169,12 @@ constexpr int stage_bytes() {
 }
 
 struct TileCoord {
-    int n, t0, h0, w0, n_tile;
+    int n, t0, h0, w0, n_tile, slice;
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile) {
     TileCoord c;
+    c.slice = tile % p.k_slices;
+    tile /= p.k_slices;
     c.n_tile = tile % p.n_tiles_n;
     int m = tile / p.n_tiles_n;
     c.w0 = (m % p.tiles_w) * p.tw;
@@ -206,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_chunks = p.cin / BLOCK_K;
-    const int num_k_blocks = p.ntaps * k_chunks;
+    const int num_k_blocks = p.taps_per_slice * k_chunks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&a_map0);
@@ -244,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile);
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    const int tap = kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
+                    const int tap = tc.slice * p.taps_per_slice + kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
                     int dt = 0, dh = 0, dw = 0;
                     if (p.ntaps == 27) {
                         dt = tap / 9 - 1;
@@ -314,9 +319,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
             const TileCoord tc = decode_tile(p, tile);
             const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
             const bool valid = t < p.t && h < p.h && w < p.w;
-            float* out_row = p.out + ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
-                                      static_cast<size_t>(tc.n_tile) * BLOCK_N);
-            const float* bias = p.bias ? p.bias + tc.n_tile * BLOCK_N : nullptr;
+            float* out_row = p.out + tc.slice * p.slice_stride +
+                             ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
+                              static_cast<size_t>(tc.n_tile) * BLOCK_N);
+            const float* bias = (p.bias && tc.slice == 0) ? p.bias + tc.n_tile * BLOCK_N : nullptr;
             mbar_wait(tmem_full_bar + acc, acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -473,10 +479,34 @@ void choose_box(int t, int h, int w, int* tt, int* th, int* tw) {
         }
 }
 
+int block_n_for(int cout) { return cout % 256 == 0 ? 256 : cout % 128 == 0 ? 128 : cout % 64 == 0 ? 64 : 32; }
+
+// split-K heuristic: layers with fewer tiles than SMs are latency-bound on one tile's serial K loop; split the
+// taps over k_slices CTAs (<= 2 waves in total) -- the consumers add the partial outputs in a fixed order.
+int auto_split(const StemsegConvShape* s) {
+    if (s->kernel_size != 3) return 1;
+    int tt, th, tw;
+    choose_box(s->t, s->h, s->w, &tt, &th, &tw);
+    const long long tiles = 1ll * s->n * ((s->t + tt - 1) / tt) * ((s->h + th - 1) / th) * ((s->w + tw - 1) / tw) *
+                            (s->cout / block_n_for(s->cout));
+    const int sms = device_sm_count();
+    if (tiles >= sms) return 1;
+    int best = 1;
+    const int options[3] = {3, 9, 27};
+    for (int o : options)
+        if (tiles * o <= 2ll * sms) best = o;
+    return best;
+}
+
 }  // namespace
 }  // namespace stemseg
 
 using namespace stemseg;
+
+extern "C" int32_t stemseg_conv3d_auto_split(const StemsegConvShape* s) {
+    if (s == nullptr || s->n < 1 || s->t < 1 || s->h < 1 || s->w < 1 || s->cout < 32) return 1;
+    return auto_split(s);
+}
 
 extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias,
                                               float* out, const StemsegConvShape* s, int32_t max_ctas,
@@ -502,9 +532,13 @@ extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void
     p.tiles_t = (p.t + p.tt - 1) / p.tt;
     p.tiles_h = (p.h + p.th - 1) / p.th;
     p.tiles_w = (p.w + p.tw - 1) / p.tw;
-    const int block_n = s->cout % 256 == 0 ? 256 : s->cout % 128 == 0 ? 128 : s->cout % 64 == 0 ? 64 : 32;
+    const int block_n = block_n_for(s->cout);
     p.n_tiles_n = s->cout / block_n;
-    const long long tiles = 1ll * p.n * p.tiles_t * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    p.k_slices = s->split_k >= 1 ? s->split_k : 1;
+    SS_REQUIRE(p.ntaps % p.k_slices == 0, "conv3d: split_k %d does not divide the %d taps", p.k_slices, p.ntaps);
+    p.taps_per_slice = p.ntaps / p.k_slices;
+    p.slice_stride = static_cast<size_t>(p.n) * p.t * p.h * p.w * p.cout;
+    const long long tiles = 1ll * p.n * p.tiles_t * p.tiles_h * p.tiles_w * p.n_tiles_n * p.k_slices;
     SS_REQUIRE(tiles < 0x7FFFFFFFll, "conv3d: too many tiles");
     p.num_tiles = static_cast<int>(tiles);
     p.out = out;

@@ -90,9 +90,20 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int 
 // Replaces the statistics pass of nn.GroupNorm(32, C) (model_builder.py:34; embedding_decoder.py:22,...).
 // Deterministic: fixed chunking, fixed reduction order, final combination in double.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kStatsChunk = 2048;     // voxels per block
+constexpr int kStatsChunk = 128;      // voxels per block
+
+// x may be stored as `slices` split-K partial sums [slices][n][spatial][c] that are added (fixed order) on read
+__device__ __forceinline__ float4 load_sum_slices(const float4* p, size_t slice_stride4, int slices) {
+    float4 a = __ldg(p);
+    for (int s = 1; s < slices; ++s) {
+        const float4 b = __ldg(p + s * slice_stride4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    return a;
+}
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, long long spatial, int c,
+                                                         int slices, size_t slice_stride,
                                                          float* __restrict__ partial /*[n][chunks][c][2]*/,
                                                          int chunks) {
     extern __shared__ float s_acc[];                 // [rows][c][2]
@@ -104,20 +115,18 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
     long long v1 = v0 + kStatsChunk;
     if (v1 > spatial) v1 = spatial;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < rows) {
-        const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * c) + q;
-        for (long long v = v0 + r; v < v1; v += rows) {
-            const float4 a = __ldg(base + v * quads);
-            s[0] += a.x; ss[0] += a.x * a.x;
-            s[1] += a.y; ss[1] += a.y * a.y;
-            s[2] += a.z; ss[2] += a.z * a.z;
-            s[3] += a.w; ss[3] += a.w * a.w;
-        }
+    const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * c) + q;
+    for (long long v = v0 + r; v < v1; v += rows) {
+        const float4 a = load_sum_slices(base + v * quads, slice_stride / 4, slices);
+        s[0] += a.x; ss[0] += a.x * a.x;
+        s[1] += a.y; ss[1] += a.y * a.y;
+        s[2] += a.z; ss[2] += a.z * a.z;
+        s[3] += a.w; ss[3] += a.w * a.w;
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            s_acc[(r * c + 4 * q + k) * 2 + 0] = s[k];
-            s_acc[(r * c + 4 * q + k) * 2 + 1] = ss[k];
-        }
+    for (int k = 0; k < 4; ++k) {
+        s_acc[(r * c + 4 * q + k) * 2 + 0] = s[k];
+        s_acc[(r * c + 4 * q + k) * 2 + 1] = ss[k];
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -174,6 +183,7 @@ template <bool POOL>
 __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int n, int t, int h, int w, int c, int cpg, int t_out,
+                                                           int slices, size_t slice_stride,
                                                            __nv_bfloat16* __restrict__ dst, size_t plane_elems,
                                                            int planes) {
     const int quads = c / 4;
@@ -209,8 +219,9 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
                     for (int dw = -1; dw <= 1; ++dw) {
                         const int wi = ww + dw;
                         if (wi < 0 || wi >= w) continue;
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(
-                                                   x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * c) + q);
+                        const float4 a = load_sum_slices(
+                            reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * c) + q,
+                            slice_stride / 4, slices);
                         acc[0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
                         acc[1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
                         acc[2] += fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
@@ -221,8 +232,9 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] *= (1.0f / 27.0f);
         } else {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(
-                                       x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * c) + q);
+            const float4 a = load_sum_slices(
+                reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * c) + q,
+                slice_stride / 4, slices);
             acc[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
             acc[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
             acc[2] = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
@@ -324,7 +336,12 @@ __device__ __forceinline__ float linspace_value(float end_abs, int steps, int i)
     return i < steps / 2 ? (-end_abs + step * static_cast<float>(i)) : (end_abs - step * static_cast<float>(steps - 1 - i));
 }
 
-__global__ void __launch_bounds__(128) head_out_kernel(const float* __restrict__ z, const float* __restrict__ ylow,
+// One warp per group of 32 consecutive voxels: for each voxel the 32 lanes read the channel row cooperatively
+// (coalesced 16-byte loads), every output is a warp-shuffle reduction, lane i keeps the outputs of voxel i so the
+// channels-first stores are coalesced along W.
+constexpr int kHeadMaxOut = 64;
+
+__global__ void __launch_bounds__(256) head_out_kernel(const float* __restrict__ z, const float* __restrict__ ylow,
                                                        int n, int t, int h, int w, int c, int st, int tl, int hl,
                                                        int wl, const float* __restrict__ wout /*[J][c]*/,
                                                        const float* __restrict__ bout /*[J] or null*/,
@@ -338,56 +355,84 @@ __global__ void __launch_bounds__(128) head_out_kernel(const float* __restrict__
     __syncthreads();
     const long long spatial = 1ll * t * h * w;
     const long long total = 1ll * n * spatial;
-    const int quads = c / 4;
-    for (long long v = blockIdx.x * 1ll * blockDim.x + threadIdx.x; v < total; v += 1ll * gridDim.x * blockDim.x) {
-        long long r = v;
-        const int wo = static_cast<int>(r % w); r /= w;
-        const int ho = static_cast<int>(r % h); r /= h;
-        const int to = static_cast<int>(r % t);
-        const int nn = static_cast<int>(r / t);
-        const Tri tr = make_tri(nn, to, ho, wo, st, tl, hl, wl, c);
-        const float4* zrow = reinterpret_cast<const float4*>(z + static_cast<size_t>(v) * c);
+    const int quads = c / 4;                               // <= 64
+    const int lane = threadIdx.x & 31;
+    const long long warps = 1ll * gridDim.x * (blockDim.x >> 5);
+    const long long groups = (total + 31) / 32;
+    for (long long g = 1ll * blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < groups; g += warps) {
+        const long long vbase = g * 32;
         for (int j0 = 0; j0 < j_total; j0 += kHeadJChunk) {
-            float acc[kHeadJChunk];
+            float mine[kHeadJChunk];
 #pragma unroll
-            for (int j = 0; j < kHeadJChunk; ++j) acc[j] = 0.f;
-            for (int q = 0; q < quads; ++q) {
-                const float4 zz = __ldg(zrow + q);
-                float xv[4] = {zz.x, zz.y, zz.z, zz.w};
+            for (int j = 0; j < kHeadJChunk; ++j) mine[j] = 0.f;
+            for (int i = 0; i < 32; ++i) {
+                const long long v = vbase + i;
+                if (v >= total) break;                       // warp-uniform
+                long long r = v;
+                const int wo = static_cast<int>(r % w); r /= w;
+                const int ho = static_cast<int>(r % h); r /= h;
+                const int to = static_cast<int>(r % t);
+                const int nn = static_cast<int>(r / t);
+                const Tri tr = make_tri(nn, to, ho, wo, st, tl, hl, wl, c);
+                float acc[kHeadJChunk];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (tr.wgt[k] != 0.f) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(ylow + tr.off[k]) + q);
-                        xv[0] = fmaf(tr.wgt[k], a.x, xv[0]);
-                        xv[1] = fmaf(tr.wgt[k], a.y, xv[1]);
-                        xv[2] = fmaf(tr.wgt[k], a.z, xv[2]);
-                        xv[3] = fmaf(tr.wgt[k], a.w, xv[3]);
+                for (int j = 0; j < kHeadJChunk; ++j) acc[j] = 0.f;
+                for (int q = lane; q < quads; q += 32) {
+                    const float4 zz = __ldg(reinterpret_cast<const float4*>(z + static_cast<size_t>(v) * c) + q);
+                    float xv[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (tr.wgt[k] != 0.f) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(ylow + tr.off[k]) + q);
+                            xv[0] = fmaf(tr.wgt[k], a.x, xv[0]);
+                            xv[1] = fmaf(tr.wgt[k], a.y, xv[1]);
+                            xv[2] = fmaf(tr.wgt[k], a.z, xv[2]);
+                            xv[3] = fmaf(tr.wgt[k], a.w, xv[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kHeadJChunk; ++j) {
+                        if (j0 + j < j_total) {
+                            const float4 wr = *reinterpret_cast<const float4*>(s_w + (j0 + j) * c + 4 * q);
+                            acc[j] = fmaf(xv[0], wr.x, acc[j]);
+                            acc[j] = fmaf(xv[1], wr.y, acc[j]);
+                            acc[j] = fmaf(xv[2], wr.z, acc[j]);
+                            acc[j] = fmaf(xv[3], wr.w, acc[j]);
+                        }
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < kHeadJChunk; ++j) {
                     if (j0 + j < j_total) {
-                        const float* wr = s_w + (j0 + j) * c + 4 * q;
-                        acc[j] = fmaf(xv[0], wr[0], acc[j]);
-                        acc[j] = fmaf(xv[1], wr[1], acc[j]);
-                        acc[j] = fmaf(xv[2], wr[2], acc[j]);
-                        acc[j] = fmaf(xv[3], wr[3], acc[j]);
+                        float a = acc[j];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                        if (lane == i) mine[j] = a;
                     }
                 }
             }
+            const long long v = vbase + lane;
+            if (v < total) {
+                long long r = v;
+                const int wo = static_cast<int>(r % w); r /= w;
+                const int ho = static_cast<int>(r % h); r /= h;
+                const int to = static_cast<int>(r % t);
+                const int nn = static_cast<int>(r / t);
 #pragma unroll
-            for (int j = 0; j < kHeadJChunk; ++j) {
-                const int jj = j0 + j;
-                if (jj >= j_total) break;
-                float val = acc[j] + s_b[jj];
-                const int a = act[jj];
-                if (a == 1) val = tanhf(0.25f * val);
-                else if (a == 2) val = 1.0f / (1.0f + expf(-val));
-                const int cd = coord[jj];
-                if (cd == 1) val += linspace_value(t_abs, t, to);
-                else if (cd == 2) val += linspace_value(y_abs, h, ho);
-                else if (cd == 3) val += linspace_value(x_abs, w, wo);
-                out[(static_cast<size_t>(nn) * j_total + jj) * spatial + (v - static_cast<long long>(nn) * spatial)] = val;
+                for (int j = 0; j < kHeadJChunk; ++j) {
+                    const int jj = j0 + j;
+                    if (jj < j_total) {
+                        float val = mine[j] + s_b[jj];
+                        const int a = act[jj];
+                        if (a == 1) val = tanhf(0.25f * val);
+                        else if (a == 2) val = 1.0f / (1.0f + expf(-val));
+                        const int cd = coord[jj];
+                        if (cd == 1) val += linspace_value(t_abs, t, to);
+                        else if (cd == 2) val += linspace_value(y_abs, h, ho);
+                        else if (cd == 3) val += linspace_value(x_abs, w, wo);
+                        out[(static_cast<size_t>(nn) * j_total + jj) * spatial + (v - static_cast<long long>(nn) * spatial)] = val;
+                    }
+                }
             }
         }
     }
@@ -447,9 +492,10 @@ extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial,
     return align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
 }
 
-extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t n, int64_t spatial, int32_t c,
+extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int32_t n, int64_t spatial, int32_t c,
                                             int32_t channels_per_group, float eps, float* mean_rstd,
                                             void* workspace, size_t workspace_bytes, void* stream_) {
+    SS_REQUIRE(slices >= 1 && slices <= 27, "group_norm_stats: slices out of range");
     SS_REQUIRE(x && mean_rstd && workspace, "group_norm_stats: null pointer");
     SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "group_norm_stats: bad group size");
@@ -466,15 +512,16 @@ extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t n, int64_t s
     const int threads = quads * rows;
     const size_t smem = static_cast<size_t>(rows) * c * 2 * sizeof(float);
     SS_REQUIRE(threads <= 1024 && smem <= 48 * 1024, "group_norm_stats: channel count %d unsupported", c);
-    gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, static_cast<float*>(workspace),
-                                                                  chunks);
+    gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, slices,
+                                                                  static_cast<size_t>(n) * spatial * c,
+                                                                  static_cast<float*>(workspace), chunks);
     gn_finalize_kernel<<<dim3(c / channels_per_group, n), 128, 0, stream>>>(
         static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, mean_rstd);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
 
-extern "C" int32_t stemseg_norm_relu_pool(const float* x, const float* mean_rstd, const float* gamma,
+extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t slices, const float* mean_rstd, const float* gamma,
                                           const float* beta, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
                                           int32_t channels_per_group, int32_t pool, void* dst_planes,
                                           int32_t planes, void* stream_) {
@@ -482,20 +529,24 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, const float* mean_rstd
     SS_REQUIRE((mean_rstd == nullptr) == (gamma == nullptr) && (gamma == nullptr) == (beta == nullptr),
                "norm_relu_pool: mean_rstd/gamma/beta must all be given or all be null");
     SS_REQUIRE(planes == 1 || planes == 2, "norm_relu_pool: planes must be 1 or 2");
+    SS_REQUIRE(slices >= 1 && slices <= 27, "norm_relu_pool: slices out of range");
     SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "norm_relu_pool: bad group size");
     SS_REQUIRE(aligned16(x) && aligned16(dst_planes), "norm_relu_pool: pointers must be 16-byte aligned");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int t_out = pool ? (t - 1) / 2 + 1 : t;
     const size_t plane_elems = static_cast<size_t>(n) * t_out * h * w * c;
+    const size_t slice_stride = static_cast<size_t>(n) * t * h * w * c;
     const long long total = 1ll * n * t_out * h * w * (c / 4);
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
     if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, dst, plane_elems, planes);
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, slices, slice_stride, dst,
+            plane_elems, planes);
     else
         gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, dst, plane_elems, planes);
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, slices, slice_stride, dst,
+            plane_elems, planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
@@ -538,7 +589,7 @@ extern "C" int32_t stemseg_head_output(const float* z, const float* y_low, int32
     const float x_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(w) / static_cast<double>(h)));
     const float y_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(h) / static_cast<double>(w)));
     const long long total = 1ll * n * t * h * w;
-    head_out_kernel<<<grid_for(total, 128, 16), 128, smem, stream>>>(z, y_low, n, t, h, w, c, t_scale, t / t_scale,
+    head_out_kernel<<<grid_for((total + 31) / 32 * 32 / 8, 32, 8), 256, smem, stream>>>(z, y_low, n, t, h, w, c, t_scale, t / t_scale,
                                                                       h / 2, w / 2, out_weight, out_bias, activation,
                                                                       coordinate, n_out, x_abs, y_abs, time_scale,
                                                                       out);

@@ -101,16 +101,26 @@ def pack_activation(x, planes):
     return Planes(dst, n, t, h, w, c)
 
 
-def conv3d(act, packed, max_ctas=0):
-    """Planes x PackedConv -> fp32 NDHWC tensor [n,t,h,w,cout] (tcgen05 implicit GEMM)."""
+def conv3d(act, packed, max_ctas=0, allow_split=False):
+    """Planes x PackedConv -> fp32 NDHWC tensor [n,t,h,w,cout] (tcgen05 implicit GEMM).
+
+    With allow_split the library may split the taps over several CTAs for layers with fewer tiles than SMs; the
+    result is then [split_k, n, t, h, w, cout] partial sums (added by the GroupNorm kernels)."""
     lib = _lib.load()
     if act.c != packed.cin:
         raise ValueError("conv input has %d channels, weights expect %d" % (act.c, packed.cin))
     if act.planes != packed.planes_tensor.shape[0]:
         raise ValueError("activation / weight precision mismatch")
-    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes)
+    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes,
+                                  1)
     with torch.cuda.device(act.tensor.device):
-        out = torch.empty((act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32, device=act.tensor.device)
+        if allow_split:
+            shape.split_k = lib.stemseg_conv3d_auto_split(shape)
+            out = torch.empty((shape.split_k, act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
+                              device=act.tensor.device)
+        else:
+            out = torch.empty((act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
+                              device=act.tensor.device)
         ev = None
         if PROFILE_EVENTS is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -126,9 +136,12 @@ def conv3d(act, packed, max_ctas=0):
 
 
 def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes):
-    """fp32 NDHWC conv output -> relu(GN(y)) [-> avgpool] as Planes.  gamma None = no normalisation."""
+    """fp32 NDHWC conv output ([split_k,] n,t,h,w,c) -> relu(GN(y)) [-> avgpool] as Planes.  gamma None = no norm."""
     lib = _lib.load()
-    n, t, h, w, c = y.shape
+    slices = 1
+    if y.dim() == 6:
+        slices = y.shape[0]
+    n, t, h, w, c = y.shape[-5:]
     dev = y.device
     with torch.cuda.device(dev):
         mean_rstd, cpg = None, 1
@@ -139,12 +152,12 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes):
             ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             mean_rstd = torch.empty((n, num_groups, 2), dtype=torch.float32, device=dev)
-            _check(lib.stemseg_group_norm_stats(_lib.ptr(y), n, t * h * w, c, cpg, float(eps), _lib.ptr(mean_rstd),
-                                                _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+            _check(lib.stemseg_group_norm_stats(_lib.ptr(y), slices, n, t * h * w, c, cpg, float(eps),
+                                                _lib.ptr(mean_rstd), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
-        _check(lib.stemseg_norm_relu_pool(_lib.ptr(y), _lib.ptr(mean_rstd), _lib.ptr(gamma), _lib.ptr(beta), n, t, h, w,
-                                          c, cpg, 1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
+        _check(lib.stemseg_norm_relu_pool(_lib.ptr(y), slices, _lib.ptr(mean_rstd), _lib.ptr(gamma), _lib.ptr(beta), n, t,
+                                          h, w, c, cpg, 1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
     return Planes(dst, n, t_out, h, w, c)
 
 
@@ -227,9 +240,9 @@ def run_trunk_and_outputs(weights, feats_32_16_8_4, num_frames, num_groups, eps,
         a = pack_activation(feat, planes)
         for j in range(n_stages):
             conv, gamma, beta = weights.stages[name][j]
-            y = conv3d(a, conv)
+            y = conv3d(a, conv, allow_split=True)
             if trace is not None:
-                trace["%s.%d.conv" % (name, 4 * j)] = y
+                trace["%s.%d.conv" % (name, 4 * j)] = y.sum(0) if y.dim() == 6 else y
             a = group_norm_relu_pool(y, gamma, beta, num_groups, eps, pools[j] and name != "block_4x", planes)
         branch.append(a)
     x = branch[0]
