@@ -168,15 +168,17 @@ int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_pl
 
 /* GroupNorm statistics of an NDHWC fp32 tensor: mean_rstd[n][c/channels_per_group][2] (biased variance, eps inside
  * the sqrt) -- nn.GroupNorm(32, C) (model_builder.py:34). Deterministic (fixed reduction order).
- * x may be `slices` split-K partial sums [slices][n][spatial][c] (see StemsegConvShape.split_k). */
+ * x may be `slices` split-K partial sums [slices][n][spatial][row_stride] (see StemsegConvShape.split_k);
+ * row_stride >= c is the element distance between voxels, so x can be a channel slice of a wider (multi-head) conv
+ * output. */
 size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
-int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int32_t n, int64_t spatial, int32_t c,
+int32_t stemseg_group_norm_stats(const float* x, int32_t row_stride, int32_t slices, int32_t n, int64_t spatial, int32_t c,
                                  int32_t channels_per_group, float eps, float* mean_rstd, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
 /* relu(group_norm(x)) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
  * (embedding_decoder.py:22-24; common.py:8-24).  mean_rstd/gamma/beta all NULL = no normalisation. */
-int32_t stemseg_norm_relu_pool(const float* x, int32_t slices, const float* mean_rstd, const float* gamma, const float* beta,
+int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* mean_rstd, const float* gamma, const float* beta,
                                int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t channels_per_group,
                                int32_t pool, void* dst_planes, int32_t planes, void* stream);
 

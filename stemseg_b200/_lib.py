@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -56,10 +56,10 @@ PROTOTYPES = {
                                              ctypes.POINTER(StemsegConvShape), c_int32, c_void_p]),
     "stemseg_conv3d_auto_split": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
-    "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_float, c_void_p,
-                                           c_void_p, c_size_t, c_void_p]),
-    "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_float,
+                                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "stemseg_upsample_add": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p, c_int32, c_void_p]),
     "stemseg_head_output": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,

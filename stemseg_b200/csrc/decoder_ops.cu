@@ -103,7 +103,7 @@ __device__ __forceinline__ float4 load_sum_slices(const float4* p, size_t slice_
 }
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, long long spatial, int c,
-                                                         int slices, size_t slice_stride,
+                                                         int row_stride, int slices, size_t slice_stride,
                                                          float* __restrict__ partial /*[n][chunks][c][2]*/,
                                                          int chunks) {
     extern __shared__ float s_acc[];                 // [rows][c][2]
@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
     long long v1 = v0 + kStatsChunk;
     if (v1 > spatial) v1 = spatial;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * c) + q;
+    const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * row_stride) + q;
+    const int row_quads = row_stride / 4;
     for (long long v = v0 + r; v < v1; v += rows) {
-        const float4 a = load_sum_slices(base + v * quads, slice_stride / 4, slices);
+        const float4 a = load_sum_slices(base + v * row_quads, slice_stride / 4, slices);
         s[0] += a.x; ss[0] += a.x * a.x;
         s[1] += a.y; ss[1] += a.y * a.y;
         s[2] += a.z; ss[2] += a.z * a.z;
@@ -183,7 +184,7 @@ template <bool POOL>
 __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int n, int t, int h, int w, int c, int cpg, int t_out,
-                                                           int slices, size_t slice_stride,
+                                                           int row_stride, int slices, size_t slice_stride,
                                                            __nv_bfloat16* __restrict__ dst, size_t plane_elems,
                                                            int planes) {
     const int quads = c / 4;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
                         const int wi = ww + dw;
                         if (wi < 0 || wi >= w) continue;
                         const float4 a = load_sum_slices(
-                            reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * c) + q,
+                            reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * row_stride) + q,
                             slice_stride / 4, slices);
                         acc[0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
                         acc[1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
             for (int k = 0; k < 4; ++k) acc[k] *= (1.0f / 27.0f);
         } else {
             const float4 a = load_sum_slices(
-                reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * c) + q,
+                reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * row_stride) + q,
                 slice_stride / 4, slices);
             acc[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
             acc[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
@@ -492,10 +493,12 @@ extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial,
     return align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
 }
 
-extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int32_t n, int64_t spatial, int32_t c,
-                                            int32_t channels_per_group, float eps, float* mean_rstd,
+extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t row_stride, int32_t slices, int32_t n,
+                                            int64_t spatial, int32_t c, int32_t channels_per_group, float eps,
+                                            float* mean_rstd,
                                             void* workspace, size_t workspace_bytes, void* stream_) {
     SS_REQUIRE(slices >= 1 && slices <= 27, "group_norm_stats: slices out of range");
+    SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "group_norm_stats: bad row stride");
     SS_REQUIRE(x && mean_rstd && workspace, "group_norm_stats: null pointer");
     SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "group_norm_stats: bad group size");
@@ -512,8 +515,8 @@ extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int3
     const int threads = quads * rows;
     const size_t smem = static_cast<size_t>(rows) * c * 2 * sizeof(float);
     SS_REQUIRE(threads <= 1024 && smem <= 48 * 1024, "group_norm_stats: channel count %d unsupported", c);
-    gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, slices,
-                                                                  static_cast<size_t>(n) * spatial * c,
+    gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, row_stride, slices,
+                                                                  static_cast<size_t>(n) * spatial * row_stride,
                                                                   static_cast<float*>(workspace), chunks);
     gn_finalize_kernel<<<dim3(c / channels_per_group, n), 128, 0, stream>>>(
         static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, mean_rstd);
@@ -521,7 +524,8 @@ extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t slices, int3
     return STEMSEG_OK;
 }
 
-extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t slices, const float* mean_rstd, const float* gamma,
+extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* mean_rstd,
+                                          const float* gamma,
                                           const float* beta, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
                                           int32_t channels_per_group, int32_t pool, void* dst_planes,
                                           int32_t planes, void* stream_) {
@@ -530,23 +534,24 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t slices, const 
                "norm_relu_pool: mean_rstd/gamma/beta must all be given or all be null");
     SS_REQUIRE(planes == 1 || planes == 2, "norm_relu_pool: planes must be 1 or 2");
     SS_REQUIRE(slices >= 1 && slices <= 27, "norm_relu_pool: slices out of range");
+    SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "norm_relu_pool: bad row stride");
     SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "norm_relu_pool: bad group size");
     SS_REQUIRE(aligned16(x) && aligned16(dst_planes), "norm_relu_pool: pointers must be 16-byte aligned");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int t_out = pool ? (t - 1) / 2 + 1 : t;
     const size_t plane_elems = static_cast<size_t>(n) * t_out * h * w * c;
-    const size_t slice_stride = static_cast<size_t>(n) * t * h * w * c;
+    const size_t slice_stride = static_cast<size_t>(n) * t * h * w * row_stride;
     const long long total = 1ll * n * t_out * h * w * (c / 4);
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
     if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, slices, slice_stride, dst,
-            plane_elems, planes);
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, row_stride, slices, slice_stride,
+            dst, plane_elems, planes);
     else
         gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, slices, slice_stride, dst,
-            plane_elems, planes);
+            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, row_stride, slices, slice_stride,
+            dst, plane_elems, planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

@@ -83,8 +83,8 @@ class Planes(object):
         return self.tensor.shape[0]
 
 
-def pack_activation(x, planes):
-    """[N,C,T,H,W] fp32 CUDA tensor (H,W contiguous; other strides free) -> Planes."""
+def pack_activation(x, planes, out=None):
+    """[N,C,T,H,W] fp32 CUDA tensor (H,W contiguous; other strides free) -> Planes (into `out` if given)."""
     lib = _lib.load()
     if x.dim() != 5:
         raise ValueError("expected a [N,C,T,H,W] feature map, got shape %s" % (tuple(x.shape),))
@@ -95,7 +95,13 @@ def pack_activation(x, planes):
     if not (x.stride(4) == 1 and x.stride(3) == w):
         x = x.contiguous()
     with torch.cuda.device(x.device):
-        dst = torch.empty((planes, n, t, h, w, c), dtype=torch.bfloat16, device=x.device)
+        if out is not None:
+            if tuple(out.tensor.shape) != (planes, n, t, h, w, c) or out.tensor.device != x.device:
+                raise ValueError("pack_activation: static buffer %s does not match input %s" % (
+                    tuple(out.tensor.shape), (planes, n, t, h, w, c)))
+            dst = out.tensor
+        else:
+            dst = torch.empty((planes, n, t, h, w, c), dtype=torch.bfloat16, device=x.device)
         _check(lib.stemseg_pack_activation(_lib.ptr(x), x.stride(0), x.stride(1), x.stride(2), n, c, t, h * w,
                                            _lib.ptr(dst), planes, _lib.stream_ptr()))
     return Planes(dst, n, t, h, w, c)
@@ -135,14 +141,17 @@ def conv3d(act, packed, max_ctas=0, allow_split=False):
     return out
 
 
-def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes):
-    """fp32 NDHWC conv output ([split_k,] n,t,h,w,c) -> relu(GN(y)) [-> avgpool] as Planes.  gamma None = no norm."""
+def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None):
+    """fp32 NDHWC conv output ([split_k,] n,t,h,w,c_total) -> relu(GN(y)) [-> avgpool] as Planes.
+
+    gamma None = no normalisation.  channel_slice=(c0, c) normalises channels [c0, c0+c) of a wider (multi-head)
+    conv output."""
     lib = _lib.load()
-    slices = 1
-    if y.dim() == 6:
-        slices = y.shape[0]
-    n, t, h, w, c = y.shape[-5:]
+    slices = y.shape[0] if y.dim() == 6 else 1
+    n, t, h, w, c_total = y.shape[-5:]
+    c0, c = (0, c_total) if channel_slice is None else channel_slice
     dev = y.device
+    x_ptr = _lib.c_void_p(y.data_ptr() + 4 * c0)
     with torch.cuda.device(dev):
         mean_rstd, cpg = None, 1
         if gamma is not None:
@@ -152,12 +161,13 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes):
             ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             mean_rstd = torch.empty((n, num_groups, 2), dtype=torch.float32, device=dev)
-            _check(lib.stemseg_group_norm_stats(_lib.ptr(y), slices, n, t * h * w, c, cpg, float(eps),
+            _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, cpg, float(eps),
                                                 _lib.ptr(mean_rstd), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+            KEEP.extend((ws, mean_rstd))
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
-        _check(lib.stemseg_norm_relu_pool(_lib.ptr(y), slices, _lib.ptr(mean_rstd), _lib.ptr(gamma), _lib.ptr(beta), n, t,
-                                          h, w, c, cpg, 1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
+        _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(mean_rstd), _lib.ptr(gamma), _lib.ptr(beta), n,
+                                          t, h, w, c, cpg, 1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
     return Planes(dst, n, t_out, h, w, c)
 
 
@@ -207,6 +217,7 @@ class TrunkWeights(object):
     """Kernel-layout weights of one head: per block a list of (PackedConv, gamma, beta); per merge (W_a, W_b)."""
 
     def __init__(self, state, inter_channels, planes, has_norm):
+        self.inter_channels = list(inter_channels)
         self.stages = {}
         for name, n_stages in BLOCKS:
             lst = []
@@ -227,32 +238,166 @@ class TrunkWeights(object):
                                 pack_conv_weight(w, planes, c_up, w.shape[1] - c_up)))
 
 
-def run_trunk_and_outputs(weights, feats_32_16_8_4, num_frames, num_groups, eps, planes, out_spec, trace=None):
-    """Forward of one head; returns the channels-first output tensor [N, J, T, H/4, W/4]."""
-    pools, tscale = pool_schedule(num_frames)
-    if len(feats_32_16_8_4) != 4:
-        raise AssertionError("Expected 4 feature maps, got {}".format(len(feats_32_16_8_4)))
-    branch = []
-    for (name, n_stages), feat in zip(BLOCKS, feats_32_16_8_4):
-        if feat.shape[2] != num_frames:
-            raise ValueError("feature map has T=%d but the head was built for NUM_FRAMES=%d" % (
-                feat.shape[2], num_frames))
-        a = pack_activation(feat, planes)
-        for j in range(n_stages):
-            conv, gamma, beta = weights.stages[name][j]
-            y = conv3d(a, conv, allow_split=True)
-            if trace is not None:
-                trace["%s.%d.conv" % (name, 4 * j)] = y.sum(0) if y.dim() == 6 else y
-            a = group_norm_relu_pool(y, gamma, beta, num_groups, eps, pools[j] and name != "block_4x", planes)
-        branch.append(a)
-    x = branch[0]
-    out = None
-    for k in range(3):
-        w_up, w_skip = weights.merges[k]
-        y_low = conv3d(x, w_up)                    # W_a . x at the low resolution
-        z = conv3d(branch[k + 1], w_skip)          # W_b . f'
-        if k < 2:
-            x = upsample_add(z, y_low, tscale[k], planes)
+class HeadSpec(object):
+    """Everything the plan needs to know about one head."""
+
+    def __init__(self, weights, out_spec, num_groups, eps):
+        self.weights, self.out_spec, self.num_groups, self.eps = weights, out_spec, num_groups, eps
+
+
+def _fuse_rows(convs):
+    """Concatenate the packed weights of several heads along the GEMM N dimension (same input, same K)."""
+    if len(convs) == 1:
+        return convs[0]
+    first = convs[0]
+    planes_tensor = torch.cat([c.planes_tensor for c in convs], dim=1).contiguous()
+    bias = None
+    if first.bias is not None:
+        bias = torch.cat([c.bias for c in convs], dim=0).contiguous()
+    return PackedConv(planes_tensor, bias, first.cin, sum(c.cout for c in convs), first.kernel_size)
+
+
+# intermediates of the plan currently being built / captured: kept alive so that no buffer is recycled while a
+# parallel branch of the CUDA graph may still read it
+KEEP = []
+
+
+class HeadSet(object):
+    """Launch plan of one or several heads that read the SAME feature pyramid (embedding + seediness (+ semseg)).
+
+    * the first 3x3x3 conv of every block reads the shared FPN tensor, so the heads' weights are concatenated along
+      the GEMM N dimension and the (dominant) im2col operand is streamed once for all heads;
+    * after packing the inputs into static bf16 planes, the whole plan is captured into ONE CUDA graph whose four
+      scale branches are independent sub-graphs (forked onto side streams during capture), so latency-bound small
+      layers overlap with the large ones and per-launch host overhead disappears;
+    * replaying a graph requires fixed addresses: inputs are packed into static plane buffers outside the graph and
+      the outputs are cloned out of the graph's private pool.
+    """
+
+    def __init__(self, specs, num_frames, planes, use_graph=True):
+        self.specs = list(specs)
+        self.num_frames = num_frames
+        self.planes = planes
+        self.use_graph = use_graph
+        self.pools, self.tscale = pool_schedule(num_frames)
+        self.first_stage = {}
+        for name, _ in BLOCKS:
+            self.first_stage[name] = _fuse_rows([s.weights.stages[name][0][0] for s in self.specs])
+        self._entries = {}
+
+    # ---- the plan itself (eager or under capture) -----------------------------------------------------------
+    def _branch(self, name, n_stages, a_in, trace):
+        """All conv stages of one scale block for every head; returns per-head Planes."""
+        y = conv3d(a_in, self.first_stage[name], allow_split=True)
+        KEEP.append(y)
+        outs, c0 = [], 0
+        for hi, spec in enumerate(self.specs):
+            conv, gamma, beta = spec.weights.stages[name][0]
+            if trace is not None and hi == trace[0]:
+                full = y.sum(0) if y.dim() == 6 else y
+                trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
+            a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
+                                     self.pools[0] and name != "block_4x", self.planes,
+                                     channel_slice=(c0, conv.cout))
+            KEEP.append(a.tensor)
+            c0 += conv.cout
+            for j in range(1, n_stages):
+                conv, gamma, beta = spec.weights.stages[name][j]
+                yj = conv3d(a, conv, allow_split=True)
+                KEEP.append(yj)
+                if trace is not None and hi == trace[0]:
+                    trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj
+                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j], self.planes)
+                KEEP.append(a.tensor)
+            outs.append(a)
+        return outs
+
+    def _plan(self, in_planes, trace=None, streams=None):
+        main = torch.cuda.current_stream()
+        branches = [None] * 4
+        if streams is None:
+            for b, (name, n_stages) in enumerate(BLOCKS):
+                branches[b] = self._branch(name, n_stages, in_planes[b], trace)
         else:
-            out = head_output(z, y_low, tscale[k], out_spec)
-    return out
+            fork = main.record_event()
+            for b, (name, n_stages) in enumerate(BLOCKS):
+                st = main if b == 3 else streams[b]
+                if st is not main:
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    branches[b] = self._branch(name, n_stages, in_planes[b], trace)
+            for b in range(3):
+                main.wait_event(streams[b].record_event())
+        outputs = []
+        for hi, spec in enumerate(self.specs):
+            x = branches[0][hi]
+            out = None
+            for k in range(3):
+                w_up, w_skip = spec.weights.merges[k]
+                y_low = conv3d(x, w_up)                      # W_a . x at the low resolution
+                z = conv3d(branches[k + 1][hi], w_skip)      # W_b . f'
+                KEEP.extend((y_low, z))
+                if k < 2:
+                    x = upsample_add(z, y_low, self.tscale[k], self.planes)
+                    KEEP.append(x.tensor)
+                else:
+                    out = head_output(z, y_low, self.tscale[k], spec.out_spec)
+            outputs.append(out)
+        return outputs
+
+    # ---- entry point -------------------------------------------------------------------------------------------
+    def run(self, feats_32_16_8_4, trace=None):
+        if len(feats_32_16_8_4) != 4:
+            raise AssertionError("Expected 4 feature maps, got {}".format(len(feats_32_16_8_4)))
+        for f in feats_32_16_8_4:
+            if f.dim() != 5 or f.shape[2] != self.num_frames:
+                raise ValueError("feature map %s does not have T=NUM_FRAMES=%d" % (tuple(f.shape), self.num_frames))
+        dev = feats_32_16_8_4[0].device
+        key = tuple((tuple(f.shape), str(f.device)) for f in feats_32_16_8_4)
+        global KEEP
+        if trace is not None or not self.use_graph:
+            KEEP = []
+            with torch.cuda.device(dev):
+                in_planes = [pack_activation(f, self.planes) for f in feats_32_16_8_4]
+                outs = self._plan(in_planes, trace=trace)
+            KEEP = []
+            return outs
+        entry = self._entries.get(key)
+        with torch.cuda.device(dev):
+            if entry is None:
+                entry = self._capture(feats_32_16_8_4, dev)
+                self._entries[key] = entry
+            for f, pl in zip(feats_32_16_8_4, entry["in_planes"]):
+                pack_activation(f, self.planes, out=pl)
+            entry["graph"].replay()
+            _lib.KERNEL_LAUNCHES[0] += entry["kernels"]
+            return [o.clone() for o in entry["outputs"]]
+
+    def _capture(self, feats, dev):
+        global KEEP
+        in_planes = [pack_activation(f, self.planes) for f in feats]
+        # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, ...) before capturing
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            KEEP = []
+            self._plan(in_planes)
+            KEEP = []
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        KEEP = []
+        before = _lib.KERNEL_LAUNCHES[0]
+        with torch.cuda.graph(graph):
+            outputs = self._plan(in_planes, streams=streams)
+        kernels = _lib.KERNEL_LAUNCHES[0] - before
+        keep, KEEP = KEEP, []
+        return {"graph": graph, "in_planes": in_planes, "outputs": outputs, "keep": keep, "kernels": kernels,
+                "streams": streams}
+
+
+def run_trunk_and_outputs(weights, feats_32_16_8_4, num_frames, num_groups, eps, planes, out_spec, trace=None):
+    """Eager forward of one head (no graph); returns the channels-first output tensor [N, J, T, H/4, W/4]."""
+    hs = HeadSet([HeadSpec(weights, out_spec, num_groups, eps)], num_frames, planes, use_graph=False)
+    return hs.run(feats_32_16_8_4, trace=None if trace is None else (0, trace))[0]

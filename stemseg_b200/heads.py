@@ -86,6 +86,8 @@ class _SqueezeExpandTrunk(nn.Module):
                 raise ValueError("channel counts must be multiples of 32 (got %d)" % ch)
         self._packed = None
         self._packed_key = None
+        self._head_set = None
+        self.use_cuda_graph = True      # capture the launch plan per input shape (set False to launch eagerly)
 
     # ---- weight repacking (lazy, invalidated when a parameter is modified or moved) ------------------------
     def _trunk_state(self):
@@ -97,15 +99,24 @@ class _SqueezeExpandTrunk(nn.Module):
     def _output_spec(self, state):
         raise NotImplementedError
 
-    def _get_packed(self):
+    def head_spec(self):
+        """Kernel-layout weights of this head (repacked when a parameter changes); shared with linked HeadSets."""
         key = self._cache_key()
         if self._packed is None or self._packed_key != key:
             state = self._trunk_state()
             planes = D.PRECISION_PLANES[self.precision]
             weights = D.TrunkWeights(state, self.inter_channels, planes, self._has_norm)
-            self._packed = (weights, self._output_spec(state))
+            self._packed = D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps)
             self._packed_key = key
+            self._head_set = None
         return self._packed
+
+    def _get_head_set(self):
+        spec = self.head_spec()
+        if getattr(self, "_head_set", None) is None:
+            self._head_set = D.HeadSet([spec], self.num_frames, D.PRECISION_PLANES[self.precision],
+                                       use_graph=self.use_cuda_graph)
+        return self._head_set
 
     def _run(self, feats_32_16_8_4, trace=None):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
@@ -113,9 +124,8 @@ class _SqueezeExpandTrunk(nn.Module):
             raise NotImplementedError("the CUDA decoder is inference-only in this round (backward kernels are a "
                                       "'next' row, SURVEY.md §8f); call it under torch.no_grad()")
         with torch.no_grad():
-            weights, spec = self._get_packed()
-            return D.run_trunk_and_outputs(weights, feats_32_16_8_4, self.num_frames, self._num_groups, self._eps,
-                                           D.PRECISION_PLANES[self.precision], spec, trace=trace)
+            head_set = self._get_head_set()
+            return head_set.run(feats_32_16_8_4, trace=None if trace is None else (0, trace))[0]
 
 
 @EMBEDDING_HEAD_REGISTRY.add("squeeze_expand_decoder")

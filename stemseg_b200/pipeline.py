@@ -29,6 +29,29 @@ class SubclipPipeline(object):
         self.semseg_scales = tuple(semseg_scales)
         if seediness_head is None and embedding_head.seediness_channels == 0:
             raise ValueError("no seediness source: give a seediness head or an embedding head with seediness_output")
+        self.fuse_heads = True          # run all heads as one HeadSet (shared im2col operand, one CUDA graph)
+        self._group = None
+        self._group_key = None
+
+    def _head_group(self):
+        """One launch plan for all heads (they read the same pyramid): stemseg_b200.decoder.HeadSet."""
+        from stemseg_b200 import decoder as D
+        heads = [self.embedding_head]
+        if not self.embedding_head.seediness_channels:
+            heads.append(self.seediness_head)
+        if self.semseg_head is not None:
+            heads.append(self.semseg_head)
+        specs = [h.head_spec() for h in heads]
+        key = tuple(id(sp) for sp in specs)
+        if self._group is None or self._group_key != key:
+            e = self.embedding_head
+            for h in heads:
+                if h.num_frames != e.num_frames or h.precision != e.precision:
+                    raise ValueError("linked heads must share NUM_FRAMES and precision")
+            self._group = D.HeadSet(specs, e.num_frames, D.PRECISION_PLANES[e.precision],
+                                    use_graph=e.use_cuda_graph)
+            self._group_key = key
+        return self._group
 
     @torch.no_grad()
     def run_heads(self, features):
@@ -37,8 +60,14 @@ class SubclipPipeline(object):
         emb_in = [features[s] for s in self.embedding_scales]
         if emb_in[0].shape[0] != 1:
             raise ValueError("SubclipPipeline processes one sub-clip at a time (batch dimension must be 1)")
-        out = self.embedding_head(emb_in).squeeze(0)
         e, v = self.embedding_head.embedding_size, self.embedding_head.variance_channels
+        if self.fuse_heads and tuple(self.embedding_scales) == (32, 16, 8, 4):
+            outs = [o.squeeze(0) for o in self._head_group().run(emb_in)]
+            out = outs.pop(0)
+            seediness = out[e + v:e + v + 1] if self.embedding_head.seediness_channels else outs.pop(0)
+            semseg = outs.pop(0) if self.semseg_head is not None else None
+            return out[:e], out[e:e + v], seediness, semseg
+        out = self.embedding_head(emb_in).squeeze(0)
         embeddings, variances = out[:e], out[e:e + v]
         if self.embedding_head.seediness_channels:
             seediness = out[e + v:e + v + 1]

@@ -157,3 +157,50 @@ def test_full_size_480p_vs_oracle(t, h4, w4, cuda_device):
     with torch.no_grad():
         out = head([f.to(cuda_device) for f in feats])
     assert_close(out.cpu(), ref, case, FP32_TOL)
+
+
+def test_fused_head_group_matches_separate_heads(cuda_device):
+    """Embedding + seediness heads as one HeadSet (shared first-stage conv, one CUDA graph) == separate heads."""
+    from stemseg_b200.pipeline import build_davis_pipeline
+    pipe = build_davis_pipeline(cuda_device, num_frames=8, in_channels=64, inter_channels=(64, 64, 32, 32))
+    feats_list = do.seeded_features(5, 1, 64, 8, 24, 40)
+    feats = {s: f.to(cuda_device) for s, f in zip((32, 16, 8, 4), feats_list)}
+    with torch.no_grad():
+        e1, v1, s1, _ = pipe.run_heads(feats)
+        e1b, v1b, s1b, _ = pipe.run_heads(feats)          # graph replay
+        pipe.fuse_heads = False
+        e2, v2, s2, _ = pipe.run_heads(feats)
+    assert torch.equal(e1, e1b) and torch.equal(v1, v1b) and torch.equal(s1, s1b)
+    for a, b in ((e1, e2), (v1, v2), (s1, s2)):
+        err = (a.double() - b.double()).abs().max().item() / b.abs().max().item()
+        assert err <= 1e-6, err          # same arithmetic per output channel (N-fusion does not change K order)
+    # oracle
+    emb_sd = {k: v.detach().cpu() for k, v in pipe.embedding_head.state_dict().items()}
+    seed_sd = {k: v.detach().cpu() for k, v in pipe.seediness_head.state_dict().items()}
+    ref = do.embedding_head(emb_sd, feats_list, 8, 4, "xyff", True, False)[0]
+    ref_seed = do.seediness_head(seed_sd, feats_list, 8)[0]
+    for a, b in ((e1.cpu(), ref[:4]), (v1.cpu(), ref[4:6]), (s1.cpu(), ref_seed)):
+        err = (a.double() - b.double()).abs().max().item() / b.abs().max().item()
+        assert err <= FP32_TOL, err
+
+
+def test_graph_and_eager_agree_and_shapes_recapture(cuda_device):
+    name = "emb_xyff_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    dev = [f.to(cuda_device) for f in feats]
+    with torch.no_grad():
+        g1 = head(dev)
+        g2 = head(dev)
+        head.use_cuda_graph = False
+        head._head_set = None
+        e = head(dev)
+        head.use_cuda_graph = True
+        head._head_set = None
+        # a different spatial size builds a second graph entry
+        feats2 = do.seeded_features(99, 1, case["in_channels"], 8, 32, 24)
+        out2 = head([f.to(cuda_device) for f in feats2])
+        ref2 = do.embedding_head(sd, feats2, 8, 4, "xyff", True, True)
+    assert torch.equal(g1, g2)
+    assert torch.equal(g1, e)
+    assert_close(out2.cpu(), ref2, case, FP32_TOL)
