@@ -166,21 +166,22 @@ int32_t stemseg_conv3d_auto_split(const StemsegConvShape* shape);
 int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias, float* out,
                                    const StemsegConvShape* shape, int32_t max_ctas, void* stream);
 
-/* GroupNorm statistics of an NDHWC fp32 tensor: mean_rstd[n][c/channels_per_group][2] (biased variance, eps inside
- * the sqrt) -- nn.GroupNorm(32, C) (model_builder.py:34). Deterministic (fixed reduction order).
- * x may be `slices` split-K partial sums [slices][n][spatial][row_stride] (see StemsegConvShape.split_k);
- * row_stride >= c is the element distance between voxels, so x can be a channel slice of a wider (multi-head) conv
- * output. */
+/* GroupNorm statistics of an NDHWC fp32 tensor -> per-channel affine table scale_shift[n][c][2] with
+ *   scale = rstd * gamma, shift = beta - mean * rstd * gamma   (biased variance, eps inside the sqrt; nn.GroupNorm(32, C),
+ * model_builder.py:34).  Deterministic (fixed reduction order, final combination in double).
+ * x may be `slices` split-K partial sums [slices][n][spatial][row_stride] (see StemsegConvShape.split_k): they are
+ * added in a fixed order and THE SUM IS WRITTEN BACK INTO SLICE 0, so later passes read one slice.  row_stride >= c
+ * is the element distance between voxels, so x can be a channel slice of a wider (multi-head) conv output. */
 size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
-int32_t stemseg_group_norm_stats(const float* x, int32_t row_stride, int32_t slices, int32_t n, int64_t spatial, int32_t c,
-                                 int32_t channels_per_group, float eps, float* mean_rstd, void* workspace,
-                                 size_t workspace_bytes, void* stream);
+int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_t slices, int32_t n, int64_t spatial, int32_t c,
+                                 int32_t channels_per_group, float eps, const float* gamma, const float* beta,
+                                 float* scale_shift, void* workspace, size_t workspace_bytes, void* stream);
 
-/* relu(group_norm(x)) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
- * (embedding_decoder.py:22-24; common.py:8-24).  mean_rstd/gamma/beta all NULL = no normalisation. */
-int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* mean_rstd, const float* gamma, const float* beta,
-                               int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t channels_per_group,
-                               int32_t pool, void* dst_planes, int32_t planes, void* stream);
+/* relu(x * scale + shift) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
+ * (embedding_decoder.py:22-24; common.py:8-24).  scale_shift NULL = no normalisation (NormType Identity). */
+int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift, int32_t n,
+                               int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool, void* dst_planes,
+                               int32_t planes, void* stream);
 
 /* dst = z + trilinear_upsample(y_low, (t_scale, 2, 2), align_corners=False) -> bf16 planes; z is [n][t][h][w][c],
  * y_low [n][t/t_scale][h/2][w/2][c] (common.py:69-78; conv1x1(cat(up(x), f)) == up(W_a x) + W_b f). */
@@ -194,6 +195,19 @@ int32_t stemseg_head_output(const float* z, const float* y_low, int32_t n, int32
                             int32_t c, int32_t t_scale, const float* out_weight, const float* out_bias,
                             const int32_t* activation, const int32_t* coordinate, int32_t n_out, float time_scale,
                             float* out, void* stream);
+
+/* Fused variant of the last merge + output heads (what the plan normally runs): the 1x1x1 conv_4 GEMM
+ * (embedding_decoder.py:80,128-129) keeps its accumulator tile on the SM and its epilogue applies the output convs,
+ * activations and coordinate offsets directly -- the [n,t,h,w,c3] merge result is never written to HBM.
+ *   out[n][j][t][h][w] = act_j( W_out[j] . (W_b f4')[voxel] + up(p_low)[voxel][j] + b_j ) + coord_j
+ * with p_low = stemseg_head_lowres(W_a x_8) = the output convs applied at the low resolution (they commute with the
+ * trilinear upsampling).  Same argument meaning as stemseg_head_output. */
+int32_t stemseg_head_lowres(const float* y_low, int64_t voxels, int32_t c, const float* out_weight, int32_t n_out,
+                            float* p_low, void* stream);
+int32_t stemseg_conv1x1_head_output(const void* act_planes, const void* weight_planes, const StemsegConvShape* shape,
+                                    const float* p_low, int32_t t_scale, const float* out_weight,
+                                    const float* out_bias, const int32_t* activation, const int32_t* coordinate,
+                                    int32_t n_out, float time_scale, float* out, int32_t max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@
 //   thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> +bias -> fp32 NDHWC store).  Two TMEM accumulator
 //   stages so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
+#include "trilinear.cuh"
 
 #include <cuda.h>
 
@@ -42,6 +43,19 @@ struct ConvTcParams {
     int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n * k_slices
     float* out;                // [k_slices][n][t][h][w][cout] fp32 (partial sums when k_slices > 1)
     const float* bias;         // [cout] or nullptr
+    int num_stages;            // smem pipeline depth
+    // ---- epilogue mode 1: fused output heads (the accumulator row never leaves the SM) ----------------------
+    //   out[n][j][t][h][w] = act_j( W_out[j] . acc_row + up(p_low)[j] + b_j ) + coord_j
+    int epi_mode;              // 0 = fp32 NDHWC store (+bias), 1 = output heads
+    int head_j;                // number of outputs J
+    const float* head_w;       // [J][cout]
+    const float* head_b;       // [J] or nullptr
+    const int* head_act;       // [J] 0 identity, 1 tanh(0.25 v), 2 sigmoid
+    const int* head_coord;     // [J] 0 none, 1 t, 2 y, 3 x
+    const float* p_low;        // [n][tl][hl][wl][J] = W_out . y_low at the low resolution
+    int st, tl, hl, wl;        // trilinear geometry (t = tl*st, h = 2 hl, w = 2 wl)
+    float x_abs, y_abs, t_abs;
+    float* head_out;           // [n][J][t][h][w]
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -186,7 +200,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
     return c;
 }
 
-template <int BLOCK_N, int BLOCK_K, int PLANES, int STAGES>
+constexpr int kMaxStages = 8;
+constexpr int kHeadJChunkTc = 8;
+
+template <int BLOCK_N, int BLOCK_K, int PLANES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant__ CUtensorMap a_map1,
                const __grid_constant__ CUtensorMap b_map0, const __grid_constant__ CUtensorMap b_map1,
@@ -202,11 +219,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.num_stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+    float* s_head_w = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);    // [J][BLOCK_N] then [J] bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -313,38 +332,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;          // accumulator row == voxel index inside the tile box
         const int dw = row % p.tw, dh = (row / p.tw) % p.th, dt = row / (p.tw * p.th);
+        if (p.epi_mode == 1) {     // stage the output-conv weights in shared memory (epilogue warps only)
+            const int et = threadIdx.x - (kNumThreads - kNumEpilogueThreads);
+            for (int i = et; i < p.head_j * BLOCK_N; i += kNumEpilogueThreads) s_head_w[i] = p.head_w[i];
+            for (int i = et; i < p.head_j; i += kNumEpilogueThreads)
+                s_head_w[p.head_j * BLOCK_N + i] = p.head_b ? p.head_b[i] : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kNumEpilogueThreads) : "memory");
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord tc = decode_tile(p, tile);
             const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
             const bool valid = t < p.t && h < p.h && w < p.w;
-            float* out_row = p.out + tc.slice * p.slice_stride +
-                             ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
-                              static_cast<size_t>(tc.n_tile) * BLOCK_N);
-            const float* bias = (p.bias && tc.slice == 0) ? p.bias + tc.n_tile * BLOCK_N : nullptr;
             mbar_wait(tmem_full_bar + acc, acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * BLOCK_N);
+            if (p.epi_mode == 0) {
+                float* out_row = p.out + tc.slice * p.slice_stride +
+                                 ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
+                                  static_cast<size_t>(tc.n_tile) * BLOCK_N);
+                const float* bias = (p.bias && tc.slice == 0) ? p.bias + tc.n_tile * BLOCK_N : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c, v);
-                tmem_ld_wait();
-                if (valid) {
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c, v);
+                    tmem_ld_wait();
+                    if (valid) {
 #pragma unroll
-                    for (int q = 0; q < 32; q += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(v[q + 0]);
-                        o.y = __uint_as_float(v[q + 1]);
-                        o.z = __uint_as_float(v[q + 2]);
-                        o.w = __uint_as_float(v[q + 3]);
-                        if (bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        for (int q = 0; q < 32; q += 4) {
+                            float4 o;
+                            o.x = __uint_as_float(v[q + 0]);
+                            o.y = __uint_as_float(v[q + 1]);
+                            o.z = __uint_as_float(v[q + 2]);
+                            o.w = __uint_as_float(v[q + 3]);
+                            if (bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            *reinterpret_cast<float4*>(out_row + c + q) = o;
                         }
-                        *reinterpret_cast<float4*>(out_row + c + q) = o;
+                    }
+                }
+            } else {
+                // fused output heads: every thread owns one voxel's accumulator row
+                const int J = p.head_j;
+                const float* s_head_b = s_head_w + J * BLOCK_N;
+                Tri tr;
+                if (valid) tr = make_tri(tc.n, t, h, w, p.st, p.tl, p.hl, p.wl, J);
+                const size_t spatial = static_cast<size_t>(p.t) * p.h * p.w;
+                const size_t vox = (static_cast<size_t>(t) * p.h + h) * p.w + w;
+#pragma unroll 1
+                for (int j0 = 0; j0 < J; j0 += kHeadJChunkTc) {
+                    float a[kHeadJChunkTc];
+#pragma unroll
+                    for (int j = 0; j < kHeadJChunkTc; ++j) a[j] = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < kHeadJChunkTc; ++j) {
+                            if (j0 + j < J) {
+                                const float4* wr = reinterpret_cast<const float4*>(s_head_w + (j0 + j) * BLOCK_N + c);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 w4 = wr[q];
+                                    a[j] = fmaf(__uint_as_float(v[4 * q + 0]), w4.x, a[j]);
+                                    a[j] = fmaf(__uint_as_float(v[4 * q + 1]), w4.y, a[j]);
+                                    a[j] = fmaf(__uint_as_float(v[4 * q + 2]), w4.z, a[j]);
+                                    a[j] = fmaf(__uint_as_float(v[4 * q + 3]), w4.w, a[j]);
+                                }
+                            }
+                        }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < kHeadJChunkTc; ++j) {
+                            const int jj = j0 + j;
+                            if (jj < J) {
+                                float val = a[j] + s_head_b[jj];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if (tr.wgt[k] != 0.f) val = fmaf(tr.wgt[k], __ldg(p.p_low + tr.off[k] + jj), val);
+                                const int ac = p.head_act[jj];
+                                if (ac == 1) val = tanhf(0.25f * val);
+                                else if (ac == 2) val = 1.0f / (1.0f + expf(-val));
+                                const int cd = p.head_coord[jj];
+                                if (cd == 1) val += linspace_value(p.t_abs, p.t, t);
+                                else if (cd == 2) val += linspace_value(p.y_abs, p.h, h);
+                                else if (cd == 3) val += linspace_value(p.x_abs, p.w, w);
+                                p.head_out[(static_cast<size_t>(tc.n) * J + jj) * spatial + vox] = val;
+                            }
+                        }
                     }
                 }
             }
@@ -429,20 +511,24 @@ int encode_weight_map(CUtensorMap* map, const void* base, int64_t k_total, int64
 }
 
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemLimit = 227 * 1024;
 
 template <int BLOCK_N, int BLOCK_K, int PLANES>
-constexpr int stages_for() {
-    constexpr int s = kSmemBudget / stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
-    return s > 8 ? 8 : s;
-}
-
-template <int BLOCK_N, int BLOCK_K, int PLANES>
-int launch_variant(const CUtensorMap* maps, const ConvTcParams& p, int max_ctas, cudaStream_t stream) {
-    constexpr int STAGES = stages_for<BLOCK_N, BLOCK_K, PLANES>();
-    static_assert(STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
-    constexpr int smem_bytes = STAGES * stage_bytes<BLOCK_N, BLOCK_K, PLANES>() + 1024 /*align*/ + 256 /*barriers*/;
-    auto kernel = conv_tc_kernel<BLOCK_N, BLOCK_K, PLANES, STAGES>;
-    SS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+int launch_variant(const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaStream_t stream) {
+    constexpr int stage = stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
+    const int head_bytes = p.epi_mode == 1 ? static_cast<int>(align_up((p.head_j * BLOCK_N + p.head_j) * sizeof(float), 16)) : 0;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + head_bytes;
+    int stages = (kSmemBudget - head_bytes) / stage;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2 || stages * stage + fixed > kSmemLimit) {
+        set_error("conv_tc: tile %dx%dx%d does not fit shared memory with %d head outputs", BLOCK_N, BLOCK_K, PLANES,
+                  p.head_j);
+        return STEMSEG_ERR_UNSUPPORTED;
+    }
+    p.num_stages = stages;
+    const int smem_bytes = stages * stage + fixed;
+    auto kernel = conv_tc_kernel<BLOCK_N, BLOCK_K, PLANES>;
+    SS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     int grid = device_sm_count();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > p.num_tiles) grid = p.num_tiles;
@@ -452,7 +538,7 @@ int launch_variant(const CUtensorMap* maps, const ConvTcParams& p, int max_ctas,
 }
 
 template <int BLOCK_K, int PLANES>
-int launch_by_n(int block_n, const CUtensorMap* maps, const ConvTcParams& p, int max_ctas, cudaStream_t stream) {
+int launch_by_n(int block_n, const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaStream_t stream) {
     switch (block_n) {
         case 256: return launch_variant<256, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
         case 128: return launch_variant<128, BLOCK_K, PLANES>(maps, p, max_ctas, stream);
@@ -508,10 +594,9 @@ extern "C" int32_t stemseg_conv3d_auto_split(const StemsegConvShape* s) {
     return auto_split(s);
 }
 
-extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias,
-                                              float* out, const StemsegConvShape* s, int32_t max_ctas,
-                                              void* stream_) {
-    SS_REQUIRE(s != nullptr && act_planes && weight_planes && out, "conv3d: null pointer");
+static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, const float* bias, float* out,
+                           const StemsegConvShape* s, int32_t max_ctas, void* stream_, const ConvTcParams* head) {
+    SS_REQUIRE(s != nullptr && act_planes && weight_planes && (out || head), "conv3d: null pointer");
     SS_REQUIRE(s->planes == 1 || s->planes == 2, "conv3d: planes must be 1 or 2");
     SS_REQUIRE(s->kernel_size == 3 || s->kernel_size == 1, "conv3d: kernel_size must be 1 or 3");
     SS_REQUIRE(s->n >= 1 && s->t >= 1 && s->h >= 1 && s->w >= 1, "conv3d: empty volume");
@@ -543,6 +628,18 @@ extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void
     p.num_tiles = static_cast<int>(tiles);
     p.out = out;
     p.bias = bias;
+    p.num_stages = 0;
+    p.epi_mode = 0;
+    p.head_j = 0;
+    if (head != nullptr) {
+        SS_REQUIRE(p.n_tiles_n == 1 && p.k_slices == 1, "conv3d+heads: cout must fit one N tile (<= 256, got %d)", s->cout);
+        p.epi_mode = 1;
+        p.head_j = head->head_j; p.head_w = head->head_w; p.head_b = head->head_b;
+        p.head_act = head->head_act; p.head_coord = head->head_coord; p.p_low = head->p_low;
+        p.st = head->st; p.tl = head->tl; p.hl = head->hl; p.wl = head->wl;
+        p.x_abs = head->x_abs; p.y_abs = head->y_abs; p.t_abs = head->t_abs;
+        p.head_out = head->head_out;
+    }
 
     // BLOCK_K: 64 channels (SWIZZLE_128B) when the stage still leaves >= 3 pipeline stages, else 32 (SWIZZLE_64B)
     int block_k = (s->cin % 64 == 0) ? 64 : 32;
@@ -566,4 +663,32 @@ extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void
                              : launch_by_n<32, 2>(block_n, maps, p, max_ctas, stream);
     return block_k == 64 ? launch_by_n<64, 1>(block_n, maps, p, max_ctas, stream)
                          : launch_by_n<32, 1>(block_n, maps, p, max_ctas, stream);
+}
+
+extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias,
+                                              float* out, const StemsegConvShape* s, int32_t max_ctas,
+                                              void* stream_) {
+    return conv3d_impl(act_planes, weight_planes, bias, out, s, max_ctas, stream_, nullptr);
+}
+
+extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const void* weight_planes,
+                                               const StemsegConvShape* s, const float* p_low, int32_t t_scale,
+                                               const float* out_weight, const float* out_bias,
+                                               const int32_t* activation, const int32_t* coordinate, int32_t n_out,
+                                               float time_scale, float* out, int32_t max_ctas, void* stream_) {
+    SS_REQUIRE(s != nullptr && p_low && out_weight && activation && coordinate && out, "conv1x1_head_output: null pointer");
+    SS_REQUIRE(s->kernel_size == 1 && s->split_k <= 1, "conv1x1_head_output: the merge conv must be 1x1x1, unsplit");
+    SS_REQUIRE(t_scale == 1 || t_scale == 2, "conv1x1_head_output: temporal scale must be 1 or 2");
+    SS_REQUIRE(s->h % 2 == 0 && s->w % 2 == 0 && s->t % t_scale == 0, "conv1x1_head_output: bad upsampling geometry");
+    SS_REQUIRE(n_out >= 1 && n_out <= 64, "conv1x1_head_output: n_out %d out of range [1,64]", n_out);
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(out_weight) & 15) == 0, "conv1x1_head_output: out_weight must be 16-byte aligned");
+    ConvTcParams head;
+    head.head_j = n_out; head.head_w = out_weight; head.head_b = out_bias;
+    head.head_act = activation; head.head_coord = coordinate; head.p_low = p_low;
+    head.st = t_scale; head.tl = s->t / t_scale; head.hl = s->h / 2; head.wl = s->w / 2;
+    head.x_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(s->w) / static_cast<double>(s->h)));
+    head.y_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(s->h) / static_cast<double>(s->w)));
+    head.t_abs = time_scale;
+    head.head_out = out;
+    return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, s, max_ctas, stream_, &head);
 }

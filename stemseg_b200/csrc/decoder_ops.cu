@@ -4,6 +4,7 @@
 // All of these are HBM-bound elementwise / small-stencil passes over NDHWC tensors: vectorised (float4 / bf16x4)
 // accesses along the channel axis, no shared-memory staging needed except for the NCTHW -> NDHWC transpose.
 #include "common.cuh"
+#include "trilinear.cuh"
 
 #include <cuda_bf16.h>
 
@@ -90,9 +91,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int 
 // Replaces the statistics pass of nn.GroupNorm(32, C) (model_builder.py:34; embedding_decoder.py:22,...).
 // Deterministic: fixed chunking, fixed reduction order, final combination in double.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kStatsChunk = 128;      // voxels per block
+constexpr int kStatsMaxChunk = 256;   // voxels per block (upper bound; small layers use smaller chunks)
 
-// x may be stored as `slices` split-K partial sums [slices][n][spatial][c] that are added (fixed order) on read
+// x may be stored as `slices` split-K partial sums [slices][n][spatial][row_stride] that are added (fixed order) on
+// read; the statistics kernel writes the sum back into slice 0 so that later passes read one slice only
 __device__ __forceinline__ float4 load_sum_slices(const float4* p, size_t slice_stride4, int slices) {
     float4 a = __ldg(p);
     for (int s = 1; s < slices; ++s) {
@@ -102,8 +104,8 @@ __device__ __forceinline__ float4 load_sum_slices(const float4* p, size_t slice_
     return a;
 }
 
-__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, long long spatial, int c,
-                                                         int row_stride, int slices, size_t slice_stride,
+__global__ void __launch_bounds__(256) gn_partial_kernel(float* __restrict__ x, long long spatial, int c,
+                                                         int row_stride, int slices, size_t slice_stride, int chunk_voxels,
                                                          float* __restrict__ partial /*[n][chunks][c][2]*/,
                                                          int chunks) {
     extern __shared__ float s_acc[];                 // [rows][c][2]
@@ -111,14 +113,25 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
     const int rows = blockDim.x / quads;
     const int q = threadIdx.x % quads, r = threadIdx.x / quads;
     const int n = blockIdx.y, chunk = blockIdx.x;
-    const long long v0 = 1ll * chunk * kStatsChunk;
-    long long v1 = v0 + kStatsChunk;
+    const long long v0 = 1ll * chunk * chunk_voxels;
+    long long v1 = v0 + chunk_voxels;
     if (v1 > spatial) v1 = spatial;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* base = reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * spatial) * row_stride) + q;
+    float4* base = reinterpret_cast<float4*>(x + (static_cast<size_t>(n) * spatial) * row_stride) + q;
     const int row_quads = row_stride / 4;
     for (long long v = v0 + r; v < v1; v += rows) {
-        const float4 a = load_sum_slices(base + v * row_quads, slice_stride / 4, slices);
+        float4* p = base + v * row_quads;
+        float4 a;
+        if (slices > 1) {
+            a = *p;
+            for (int sl = 1; sl < slices; ++sl) {
+                const float4 b = __ldcs(p + sl * (slice_stride / 4));
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *p = a;                                   // reduced value replaces slice 0 (this thread owns the element)
+        } else {
+            a = *p;
+        }
         s[0] += a.x; ss[0] += a.x * a.x;
         s[1] += a.y; ss[1] += a.y * a.y;
         s[2] += a.z; ss[2] += a.z * a.z;
@@ -142,11 +155,13 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
     }
 }
 
-// one block per (group, sample)
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int chunks, int c,
+// one block per (group, sample): mean / rstd of the group and the per-channel affine table
+//   scale[ch] = rstd * gamma[ch],  shift[ch] = beta[ch] - mean * rstd * gamma[ch]
+__global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restrict__ partial, int chunks, int c,
                                                           int cpg, long long spatial, float eps,
-                                                          float* __restrict__ mean_rstd /*[n][groups][2]*/) {
-    const int g = blockIdx.x, n = blockIdx.y, groups = c / cpg;
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ scale_shift /*[n][c][2]*/) {
+    const int g = blockIdx.x, n = blockIdx.y;
     double s = 0.0, ss = 0.0;
     for (int i = threadIdx.x; i < chunks * cpg; i += blockDim.x) {
         const int chunk = i / cpg, ch = g * cpg + i % cpg;
@@ -154,25 +169,29 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
         s += p[0];
         ss += p[1];
     }
-    __shared__ double sh[2][128];
+    __shared__ double sh[2][512];
     sh[0][threadIdx.x] = s;
     sh[1][threadIdx.x] = ss;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
+    for (int o = 256; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
             sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < cpg) {
         const double cnt = static_cast<double>(spatial) * cpg;
         const double mean = sh[0][0] / cnt;
         double var = sh[1][0] / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
-        float* o = mean_rstd + (static_cast<size_t>(n) * groups + g) * 2;
-        o[0] = static_cast<float>(mean);
-        o[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const float m = static_cast<float>(mean);
+        const int ch = g * cpg + threadIdx.x;
+        float* o = scale_shift + (static_cast<size_t>(n) * c + ch) * 2;
+        const float sc = rstd * gamma[ch];
+        o[0] = sc;
+        o[1] = beta[ch] - m * sc;
     }
 }
 
@@ -181,15 +200,13 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 // Replaces GroupNorm apply + ReLU + AvgPool3d (embedding_decoder.py:22-24; common.py:8-24).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool POOL>
-__global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ mean_rstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int n, int t, int h, int w, int c, int cpg, int t_out,
+__global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
+                                                           int n, int t, int h, int w, int c, int t_out,
                                                            int row_stride, int slices, size_t slice_stride,
                                                            __nv_bfloat16* __restrict__ dst, size_t plane_elems,
                                                            int planes) {
     const int quads = c / 4;
     const long long total = 1ll * n * t_out * h * w * quads;
-    const int groups = c / cpg;
     for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
         const int q = static_cast<int>(i % quads);
         long long v = i / quads;
@@ -197,17 +214,12 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
         const int hh = static_cast<int>(v % h); v /= h;
         const int to = static_cast<int>(v % t_out);
         const int nn = static_cast<int>(v / t_out);
-        float sc[4], sh[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ch = 4 * q + k;
-            float m = 0.f, r = 1.f, g = 1.f, b = 0.f;
-            if (mean_rstd) {
-                const float* mr = mean_rstd + (static_cast<size_t>(nn) * groups + ch / cpg) * 2;
-                m = mr[0]; r = mr[1]; g = gamma[ch]; b = beta[ch];
-            }
-            sc[k] = r * g;
-            sh[k] = b - m * r * g;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (scale_shift) {
+            const float4* tab = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(nn) * c + 4 * q) * 2);
+            const float4 t0 = __ldg(tab), t1 = __ldg(tab + 1);
+            sc[0] = t0.x; sh[0] = t0.y; sc[1] = t0.z; sh[1] = t0.w;
+            sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (POOL) {
@@ -244,46 +256,6 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
         const size_t off = ((((static_cast<size_t>(nn) * t_out + to) * h + hh) * w + ww) * c) + 4 * q;
         store_planes4(dst, plane_elems, planes, off, acc);
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// trilinear (align_corners=False) source taps for integer scale 1 or 2 along one axis (common.py:69-78)
-// ---------------------------------------------------------------------------------------------------------------
-struct Tap {
-    int i0, i1;
-    float w0, w1;
-};
-__device__ __forceinline__ Tap axis_tap(int dst, int scale, int src_size) {
-    Tap tp;
-    if (scale == 1) {
-        tp.i0 = tp.i1 = dst; tp.w0 = 1.f; tp.w1 = 0.f;
-        return tp;
-    }
-    float s = (static_cast<float>(dst) + 0.5f) * 0.5f - 0.5f;       // area_pixel_compute_source_index
-    if (s < 0.f) s = 0.f;
-    tp.i0 = static_cast<int>(s);
-    tp.i1 = tp.i0 + (tp.i0 < src_size - 1 ? 1 : 0);
-    tp.w1 = s - static_cast<float>(tp.i0);
-    tp.w0 = 1.f - tp.w1;
-    return tp;
-}
-
-struct Tri {
-    size_t off[8];
-    float wgt[8];
-};
-__device__ __forceinline__ Tri make_tri(int nn, int to, int ho, int wo, int st, int tl, int hl, int wl, int c) {
-    const Tap a = axis_tap(to, st, tl), b = axis_tap(ho, 2, hl), d = axis_tap(wo, 2, wl);
-    Tri r;
-    const int ti[2] = {a.i0, a.i1}, hi[2] = {b.i0, b.i1}, wi[2] = {d.i0, d.i1};
-    const float tw[2] = {a.w0, a.w1}, hw_[2] = {b.w0, b.w1}, ww[2] = {d.w0, d.w1};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int x = i & 1, y = (i >> 1) & 1, z = i >> 2;
-        r.off[i] = (((static_cast<size_t>(nn) * tl + ti[z]) * hl + hi[y]) * wl + wi[x]) * c;
-        r.wgt[i] = tw[z] * hw_[y] * ww[x];
-    }
-    return r;
 }
 
 // K3b: out = z + upsample(y_low)  -> bf16 planes (input of the next 1x1 merge GEMM)
@@ -329,13 +301,6 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kHeadMaxC = 256;
 constexpr int kHeadJChunk = 8;
-
-__device__ __forceinline__ float linspace_value(float end_abs, int steps, int i) {
-    // torch.linspace(-a, a, steps) fp32: start + i*step for the first half, end - (steps-1-i)*step for the second
-    if (steps == 1) return -end_abs;
-    const float step = (end_abs - (-end_abs)) / static_cast<float>(steps - 1);
-    return i < steps / 2 ? (-end_abs + step * static_cast<float>(i)) : (end_abs - step * static_cast<float>(steps - 1 - i));
-}
 
 // One warp per group of 32 consecutive voxels: for each voxel the 32 lanes read the channel row cooperatively
 // (coalesced 16-byte loads), every output is a warp-shuffle reduction, lane i keeps the outputs of voxel i so the
@@ -439,6 +404,30 @@ __global__ void __launch_bounds__(256) head_out_kernel(const float* __restrict__
     }
 }
 
+// p_low[v][j] = sum_c W_out[j][c] * y_low[v][c]: the output convs applied at the LOW resolution (they commute with the
+// trilinear upsampling), consumed by the fused head epilogue of the conv_4 GEMM (conv_tc.cu, epi_mode 1).
+__global__ void __launch_bounds__(256) head_lowres_kernel(const float* __restrict__ ylow, long long voxels, int c,
+                                                          const float* __restrict__ wout, int j_total,
+                                                          float* __restrict__ p_low) {
+    const long long total = voxels * j_total;
+    const int quads = c / 4;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int j = static_cast<int>(i % j_total);
+        const long long v = i / j_total;
+        const float4* row = reinterpret_cast<const float4*>(ylow + static_cast<size_t>(v) * c);
+        const float4* wr = reinterpret_cast<const float4*>(wout + static_cast<size_t>(j) * c);
+        float acc = 0.f;
+        for (int q = 0; q < quads; ++q) {
+            const float4 a = __ldg(row + q), b = __ldg(wr + q);
+            acc = fmaf(a.x, b.x, acc);
+            acc = fmaf(a.y, b.y, acc);
+            acc = fmaf(a.z, b.z, acc);
+            acc = fmaf(a.w, b.w, acc);
+        }
+        p_low[i] = acc;
+    }
+}
+
 inline unsigned grid_for(long long total, int block, int waves = 8) {
     long long blocks = (total + block - 1) / block;
     const long long cap = static_cast<long long>(device_sm_count()) * waves;
@@ -488,28 +477,38 @@ extern "C" int32_t stemseg_pack_conv_weight(const float* src, int32_t cout, int3
     return STEMSEG_OK;
 }
 
+static int stats_chunk_voxels(int64_t spatial) {
+    // enough blocks to fill the device even for the few-thousand-voxel layers
+    long long chunk = (spatial + 4ll * device_sm_count() - 1) / (4ll * device_sm_count());
+    if (chunk < 8) chunk = 8;
+    if (chunk > kStatsMaxChunk) chunk = kStatsMaxChunk;
+    return static_cast<int>(chunk);
+}
+
 extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c) {
-    const long long chunks = (spatial + kStatsChunk - 1) / kStatsChunk;
+    const long long chunks = (spatial + 7) / 8;          // upper bound over every chunk size that may be chosen
     return align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
 }
 
-extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t row_stride, int32_t slices, int32_t n,
+extern "C" int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_t slices, int32_t n,
                                             int64_t spatial, int32_t c, int32_t channels_per_group, float eps,
-                                            float* mean_rstd,
+                                            const float* gamma, const float* beta, float* scale_shift,
                                             void* workspace, size_t workspace_bytes, void* stream_) {
+    SS_REQUIRE(x && scale_shift && gamma && beta && workspace, "group_norm_stats: null pointer");
+    SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
+    SS_REQUIRE(channels_per_group >= 1 && channels_per_group <= 512 && c % channels_per_group == 0,
+               "group_norm_stats: bad group size");
     SS_REQUIRE(slices >= 1 && slices <= 27, "group_norm_stats: slices out of range");
     SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "group_norm_stats: bad row stride");
-    SS_REQUIRE(x && mean_rstd && workspace, "group_norm_stats: null pointer");
-    SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
-    SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "group_norm_stats: bad group size");
     SS_REQUIRE(aligned16(x), "group_norm_stats: x must be 16-byte aligned");
-    const size_t need = stemseg_group_norm_workspace_bytes(n, spatial, c);
+    const int chunk_voxels = stats_chunk_voxels(spatial);
+    const int chunks = static_cast<int>((spatial + chunk_voxels - 1) / chunk_voxels);
+    const size_t need = align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
     if (workspace_bytes < need) {
         set_error("group_norm_stats: workspace %zu < %zu bytes", workspace_bytes, need);
         return STEMSEG_ERR_WORKSPACE;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int chunks = static_cast<int>((spatial + kStatsChunk - 1) / kStatsChunk);
     const int quads = c / 4;
     const int rows = 256 / quads >= 1 ? 256 / quads : 1;
     const int threads = quads * rows;
@@ -517,27 +516,23 @@ extern "C" int32_t stemseg_group_norm_stats(const float* x, int32_t row_stride, 
     SS_REQUIRE(threads <= 1024 && smem <= 48 * 1024, "group_norm_stats: channel count %d unsupported", c);
     gn_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(x, spatial, c, row_stride, slices,
                                                                   static_cast<size_t>(n) * spatial * row_stride,
-                                                                  static_cast<float*>(workspace), chunks);
-    gn_finalize_kernel<<<dim3(c / channels_per_group, n), 128, 0, stream>>>(
-        static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, mean_rstd);
+                                                                  chunk_voxels, static_cast<float*>(workspace), chunks);
+    gn_finalize_kernel<<<dim3(c / channels_per_group, n), 512, 0, stream>>>(
+        static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, gamma, beta, scale_shift);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
 
-extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* mean_rstd,
-                                          const float* gamma,
-                                          const float* beta, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
-                                          int32_t channels_per_group, int32_t pool, void* dst_planes,
-                                          int32_t planes, void* stream_) {
+extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift,
+                                          int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool,
+                                          void* dst_planes, int32_t planes, void* stream_) {
     SS_REQUIRE(x && dst_planes, "norm_relu_pool: null pointer");
-    SS_REQUIRE((mean_rstd == nullptr) == (gamma == nullptr) && (gamma == nullptr) == (beta == nullptr),
-               "norm_relu_pool: mean_rstd/gamma/beta must all be given or all be null");
     SS_REQUIRE(planes == 1 || planes == 2, "norm_relu_pool: planes must be 1 or 2");
     SS_REQUIRE(slices >= 1 && slices <= 27, "norm_relu_pool: slices out of range");
     SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "norm_relu_pool: bad row stride");
     SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");
-    SS_REQUIRE(channels_per_group >= 1 && c % channels_per_group == 0, "norm_relu_pool: bad group size");
-    SS_REQUIRE(aligned16(x) && aligned16(dst_planes), "norm_relu_pool: pointers must be 16-byte aligned");
+    SS_REQUIRE(aligned16(x) && aligned16(dst_planes) && aligned16(scale_shift),
+               "norm_relu_pool: pointers must be 16-byte aligned");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int t_out = pool ? (t - 1) / 2 + 1 : t;
     const size_t plane_elems = static_cast<size_t>(n) * t_out * h * w * c;
@@ -546,12 +541,10 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
     if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, row_stride, slices, slice_stride,
-            dst, plane_elems, planes);
+            x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     else
         gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
-            x, mean_rstd, gamma, beta, n, t, h, w, c, channels_per_group, t_out, row_stride, slices, slice_stride,
-            dst, plane_elems, planes);
+            x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
@@ -598,6 +591,17 @@ extern "C" int32_t stemseg_head_output(const float* z, const float* y_low, int32
                                                                       h / 2, w / 2, out_weight, out_bias, activation,
                                                                       coordinate, n_out, x_abs, y_abs, time_scale,
                                                                       out);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_head_lowres(const float* y_low, int64_t voxels, int32_t c, const float* out_weight,
+                                       int32_t n_out, float* p_low, void* stream_) {
+    SS_REQUIRE(y_low && out_weight && p_low, "head_lowres: null pointer");
+    SS_REQUIRE(voxels >= 1 && c >= 4 && c % 4 == 0 && n_out >= 1 && n_out <= 64, "head_lowres: bad shape");
+    SS_REQUIRE(aligned16(y_low) && aligned16(out_weight), "head_lowres: pointers must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    head_lowres_kernel<<<grid_for(voxels * n_out, 256, 16), 256, 0, stream>>>(y_low, voxels, c, out_weight, n_out, p_low);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

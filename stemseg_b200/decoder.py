@@ -153,21 +153,22 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
     dev = y.device
     x_ptr = _lib.c_void_p(y.data_ptr() + 4 * c0)
     with torch.cuda.device(dev):
-        mean_rstd, cpg = None, 1
+        scale_shift = None
         if gamma is not None:
             if c % num_groups != 0:
                 raise ValueError("channels %d not divisible by %d groups" % (c, num_groups))
-            cpg = c // num_groups
             ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            mean_rstd = torch.empty((n, num_groups, 2), dtype=torch.float32, device=dev)
-            _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, cpg, float(eps),
-                                                _lib.ptr(mean_rstd), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
-            KEEP.extend((ws, mean_rstd))
+            scale_shift = torch.empty((n, c, 2), dtype=torch.float32, device=dev)
+            _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, c // num_groups, float(eps),
+                                                _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift), _lib.ptr(ws),
+                                                ws_bytes, _lib.stream_ptr()))
+            KEEP.extend((ws, scale_shift))
+            slices = 1                               # the statistics pass summed the split-K slices into slice 0
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
-        _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(mean_rstd), _lib.ptr(gamma), _lib.ptr(beta), n,
-                                          t, h, w, c, cpg, 1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
+        _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c,
+                                          1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
     return Planes(dst, n, t_out, h, w, c)
 
 
@@ -210,6 +211,29 @@ def head_output(z, y_low, t_scale, spec):
         _check(lib.stemseg_head_output(_lib.ptr(z), _lib.ptr(y_low), n, t, h, w, c, t_scale, _lib.ptr(spec.weight),
                                        _lib.ptr(spec.bias), _lib.ptr(spec.activation), _lib.ptr(spec.coordinate),
                                        spec.n_out, spec.time_scale, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def fused_merge_head_output(act, packed, y_low, t_scale, spec, max_ctas=0):
+    """Last merge + output heads in one launch: conv1x1(act) stays in TMEM, its epilogue applies the output convs.
+
+    act: Planes of f4' (the skip half of conv_4), packed: W_b, y_low: fp32 [n,tl,hl,wl,c3] = W_a . x_8."""
+    lib = _lib.load()
+    n, tl, hl, wl, c = y_low.shape
+    if (act.n, act.t, act.h, act.w) != (n, tl * t_scale, 2 * hl, 2 * wl) or packed.cout != c:
+        raise ValueError("fused_merge_head_output: low-res %s does not upsample by (%d,2,2) to %s" % (
+            tuple(y_low.shape), t_scale, (act.n, act.t, act.h, act.w, packed.cout)))
+    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, 1, act.planes, 1)
+    with torch.cuda.device(y_low.device):
+        p_low = torch.empty((n, tl, hl, wl, spec.n_out), dtype=torch.float32, device=y_low.device)
+        _check(lib.stemseg_head_lowres(_lib.ptr(y_low), n * tl * hl * wl, c, _lib.ptr(spec.weight), spec.n_out,
+                                       _lib.ptr(p_low), _lib.stream_ptr()))
+        out = torch.empty((n, spec.n_out, act.t, act.h, act.w), dtype=torch.float32, device=y_low.device)
+        _check(lib.stemseg_conv1x1_head_output(_lib.ptr(act.tensor), _lib.ptr(packed.planes_tensor), shape,
+                                               _lib.ptr(p_low), t_scale, _lib.ptr(spec.weight), _lib.ptr(spec.bias),
+                                               _lib.ptr(spec.activation), _lib.ptr(spec.coordinate), spec.n_out,
+                                               spec.time_scale, _lib.ptr(out), max_ctas, _lib.stream_ptr()))
+    KEEP.append(p_low)
     return out
 
 
@@ -279,6 +303,7 @@ class HeadSet(object):
         self.num_frames = num_frames
         self.planes = planes
         self.use_graph = use_graph
+        self.fuse_output_heads = True       # conv_4 merge GEMM + output heads in one kernel (epilogue fusion)
         self.pools, self.tscale = pool_schedule(num_frames)
         self.first_stage = {}
         for name, _ in BLOCKS:
@@ -294,7 +319,7 @@ class HeadSet(object):
         for hi, spec in enumerate(self.specs):
             conv, gamma, beta = spec.weights.stages[name][0]
             if trace is not None and hi == trace[0]:
-                full = y.sum(0) if y.dim() == 6 else y
+                full = y.sum(0) if y.dim() == 6 else y.clone()
                 trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
             a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
                                      self.pools[0] and name != "block_4x", self.planes,
@@ -306,7 +331,7 @@ class HeadSet(object):
                 yj = conv3d(a, conv, allow_split=True)
                 KEEP.append(yj)
                 if trace is not None and hi == trace[0]:
-                    trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj
+                    trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj.clone()
                 a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j], self.planes)
                 KEEP.append(a.tensor)
             outs.append(a)
@@ -335,8 +360,12 @@ class HeadSet(object):
             for k in range(3):
                 w_up, w_skip = spec.weights.merges[k]
                 y_low = conv3d(x, w_up)                      # W_a . x at the low resolution
+                KEEP.append(y_low)
+                if k == 2 and self.fuse_output_heads and w_skip.cout <= 256:
+                    out = fused_merge_head_output(branches[3][hi], w_skip, y_low, self.tscale[k], spec.out_spec)
+                    continue
                 z = conv3d(branches[k + 1][hi], w_skip)      # W_b . f'
-                KEEP.extend((y_low, z))
+                KEEP.append(z)
                 if k < 2:
                     x = upsample_add(z, y_low, self.tscale[k], self.planes)
                     KEEP.append(x.tensor)

@@ -204,3 +204,21 @@ def test_graph_and_eager_agree_and_shapes_recapture(cuda_device):
     assert torch.equal(g1, g2)
     assert torch.equal(g1, e)
     assert_close(out2.cpu(), ref2, case, FP32_TOL)
+
+
+@pytest.mark.parametrize("name", ["emb_xyff_t8", "semseg_42_t8", "emb_xytff_t16", "seediness_fullwidth_t8"])
+def test_fused_head_epilogue_matches_unfused(name, cuda_device):
+    """conv_4 GEMM with the output heads in its epilogue == separate GEMM + head kernel (same math, two paths)."""
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    dev = [f.to(cuda_device) for f in feats]
+    with torch.no_grad():
+        fused = head(dev)
+        hs = head._get_head_set()
+        hs.fuse_output_heads = False
+        hs._entries.clear()
+        unfused = head(dev)
+    assert fused.shape == unfused.shape
+    for _, sl in output_groups(case, fused.shape[1]).items():
+        a, b = fused[:, sl].double(), unfused[:, sl].double()
+        assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()
