@@ -58,7 +58,8 @@ int32_t stemseg_check_device(void);
  *   word 0            K  = number of clusters created                    (len(instance_labels), clusterers.py:121)
  *   word 1            exit reason: 0 loop ran max_instances times, 1 no unassigned point left (clusterers.py:109),
  *                                  2 best seediness < min_seediness_prob (clusterers.py:116)
- *   word 2..3         reserved
+ *   word 2            number of points clustered (differs from n_points only with n_points_dev)
+ *   word 3            reserved
  *   then int32  seed_index[max_instances]       index of the seed point of cluster k
  *   then float  centers[max_instances][E]       instance_centers (clusterers.py:124)
  *   then float  bandwidths[max_instances][E]    cat(bandwidth[seed], free_dim_bandwidths) (clusterers.py:119);
@@ -86,11 +87,14 @@ int32_t stemseg_seq_cluster_workspace_bytes(const StemsegClusterParams* params, 
  * primary     device int32 [N]  out    ordinal k of the cluster that claimed the point in the primary pass, -1 if
  *                                      none (instance_masks[k] == (primary == k), clusterers.py:145-146)
  * meta        device words      out    see above
- * Precondition N >= 1 (the N == 0 early return of clusterers.py:62-69 is host logic).
+ * n_points_dev optional device int32: the actual point count (<= params->n_points, which is then the capacity
+ *             of the buffers); lets compaction -> gather -> clustering run back to back without a host round trip.
+ *             meta word 2 reports the count that was clustered (0 points -> K = 0, exit reason 1).
+ * Precondition params->n_points >= 1 (the N == 0 early return of clusterers.py:62-69 is host logic).
  */
 int32_t stemseg_seq_cluster(const float* embeddings, const float* bandwidths, const float* seediness,
-                            const StemsegClusterParams* params, int64_t* labels, int32_t* primary, void* meta,
-                            void* workspace, size_t workspace_bytes, void* stream);
+                            const StemsegClusterParams* params, const int32_t* n_points_dev, int64_t* labels,
+                            int32_t* primary, void* meta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Host helper: largest fp32 d >= 0 with fl32(exp(-0.5 d)) > fl32(p); -1 if none, +inf if every d qualifies. */
 float stemseg_prob_threshold_to_distance(double prob_threshold);
@@ -119,11 +123,12 @@ int32_t stemseg_fg_compact_threshold(const float* values, float threshold, int64
 /*
  * src       device float [C][T*HW] channel-first map, channel stride `channel_stride` elements
  * indices   device int32 [n]
+ * n_dev     optional device int32: actual number of points (<= n, n is then the capacity of indices / dst)
  * transform 0 = copy; 1 = exp(x) * 10, the bandwidth activation of inference_model.py:148 fused into the gather
  * dst       device float [n][C] out
  */
 int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, int32_t channels, const int32_t* indices,
-                          int64_t n, int32_t transform, float* dst, void* stream);
+                          int64_t n, const int32_t* n_dev, int32_t transform, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 3-D decoder heads (SqueezingExpandDecoder x3)

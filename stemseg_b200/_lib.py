@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -41,13 +41,14 @@ PROTOTYPES = {
     "stemseg_seq_cluster_workspace_bytes": (c_int32, [ctypes.POINTER(StemsegClusterParams),
                                                       ctypes.POINTER(c_size_t)]),
     "stemseg_seq_cluster": (c_int32, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(StemsegClusterParams), c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_prob_threshold_to_distance": (c_float, [c_double]),
     "stemseg_fg_compact_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "stemseg_fg_compact": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_fg_compact_threshold": (c_int32, [c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                                c_size_t, c_void_p]),
-    "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
+                                    c_void_p]),
     "stemseg_pack_activation": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_int32, c_void_p]),
     "stemseg_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,

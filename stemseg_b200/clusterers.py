@@ -89,11 +89,6 @@ class SequentialClustering(ClustererBase):
         n, e = embeddings.shape
         if self.n_free_dims == 0:
             assert embeddings.shape == bandwidths.shape                              # clusterers.py:80-81
-        if e > _lib.STEMSEG_MAX_EMBEDDING_DIMS:
-            raise ValueError("embedding size %d > %d unsupported" % (e, _lib.STEMSEG_MAX_EMBEDDING_DIMS))
-        if bandwidths.shape[1] + self.n_free_dims != e:
-            raise ValueError("bandwidths has %d columns, expected %d (E=%d, n_free_dims=%d)" % (
-                bandwidths.shape[1], e - self.n_free_dims, e, self.n_free_dims))
 
         assert torch.is_tensor(seediness)
         seediness = seediness.reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()  # [N,1] -> [N]
@@ -101,6 +96,20 @@ class SequentialClustering(ClustererBase):
 
         return_label_masks = kwargs.get("return_label_masks", False)
 
+        pending = self.launch(embeddings, bandwidths, seediness, cluster_label_start)
+        labels, meta = self.finish(pending, return_label_masks)
+        return labels.to(input_device), meta
+
+    @torch.no_grad()
+    def launch(self, embeddings, bandwidths, seediness, cluster_label_start=1, n_points_dev=None):
+        """Enqueue the clustering kernel without synchronising (capture-safe).  All inputs are contiguous fp32 CUDA
+        tensors of a fixed *capacity* N; ``n_points_dev`` (device int32 [1]) optionally holds the actual count."""
+        n, e = embeddings.shape
+        if e > _lib.STEMSEG_MAX_EMBEDDING_DIMS:
+            raise ValueError("embedding size %d > %d unsupported" % (e, _lib.STEMSEG_MAX_EMBEDDING_DIMS))
+        if bandwidths.shape[1] + self.n_free_dims != e:
+            raise ValueError("bandwidths has %d columns, expected %d (E=%d, n_free_dims=%d)" % (
+                bandwidths.shape[1], e - self.n_free_dims, e, self.n_free_dims))
         params = _lib.StemsegClusterParams()
         params.n_points = n
         params.embedding_dims = e
@@ -127,11 +136,21 @@ class SequentialClustering(ClustererBase):
             meta = torch.empty(meta_words, dtype=torch.int32, device=self.device)
             workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=self.device)
             _lib.check(lib.stemseg_seq_cluster(
-                _lib.ptr(embeddings), _lib.ptr(bandwidths), _lib.ptr(seediness), params, _lib.ptr(labels),
-                _lib.ptr(primary), _lib.ptr(meta), _lib.ptr(workspace), ws_bytes.value, _lib.stream_ptr()))
-            meta_host = meta.cpu()                        # the one device->host sync of the call
-        self._last_primary = primary
+                _lib.ptr(embeddings), _lib.ptr(bandwidths), _lib.ptr(seediness), params, _lib.ptr(n_points_dev),
+                _lib.ptr(labels), _lib.ptr(primary), _lib.ptr(meta), _lib.ptr(workspace), ws_bytes.value,
+                _lib.stream_ptr()))
+        return {"labels": labels, "primary": primary, "meta": meta, "e": e, "label_start": int(cluster_label_start),
+                "workspace": workspace}
 
+    @torch.no_grad()
+    def finish(self, pending, return_label_masks=False):
+        """Fetch the metadata of a launched clustering (the one device->host sync) and format the reference's dict."""
+        labels, primary, e = pending["labels"], pending["primary"], pending["e"]
+        cluster_label_start = pending["label_start"]
+        meta_host = pending["meta"].cpu()
+        n_done = int(meta_host[2])
+        labels, primary = labels[:n_done], primary[:n_done]
+        self._last_primary = primary
         k = int(meta_host[0])
         mi = self.max_instances
         floats = meta_host[4 + mi:].view(torch.float32)
@@ -144,7 +163,7 @@ class SequentialClustering(ClustererBase):
         if return_label_masks:                                                      # clusterers.py:145-146
             label_masks = [(primary == i).cpu() for i in range(k)]
 
-        return labels.to(input_device), {
+        return labels, {
             'instance_labels': unique_labels,
             'instance_centers': label_centers,
             'instance_stds': label_stds,

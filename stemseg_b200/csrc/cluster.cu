@@ -27,6 +27,7 @@ struct ClusterArgs {
     const float* emb;
     const float* bw;
     const float* seed;
+    const int* n_dev;            // optional device-side point count (<= n); n is then the capacity
     long long n;
     int v;                       // learned-bandwidth columns (E - n_free)
     float free_bw[kMaxE];
@@ -139,7 +140,11 @@ __device__ __forceinline__ void publish_key(unsigned long long key, unsigned lon
 }
 
 template <int E, bool VEC>
-__global__ void __launch_bounds__(kThreads) seq_cluster_kernel(const ClusterArgs a) {
+__global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
+    if (a.n_dev != nullptr) {
+        const long long nd = *a.n_dev;
+        if (nd < a.n) a.n = nd;
+    }
     __shared__ float s_center[kMaxI][E];
     __shared__ float s_bw[kMaxI][E];
     __shared__ unsigned long long s_red[kThreads / 32];
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(const ClusterArgs
         if (threadIdx.x == 0) {
             a.meta[0] = static_cast<unsigned int>(num_clusters);
             a.meta[1] = static_cast<unsigned int>(exit_reason);
-            a.meta[2] = 0u;
+            a.meta[2] = static_cast<unsigned int>(a.n);      // points actually clustered
             a.meta[3] = 0u;
         }
         float* centers = reinterpret_cast<float*>(a.meta + 4 + a.max_inst);
@@ -303,8 +308,9 @@ extern "C" float stemseg_prob_threshold_to_distance(double prob_threshold) {
 }
 
 extern "C" int32_t stemseg_seq_cluster(const float* embeddings, const float* bandwidths, const float* seediness,
-                                       const StemsegClusterParams* p, int64_t* labels, int32_t* primary, void* meta,
-                                       void* workspace, size_t workspace_bytes, void* stream_) {
+                                       const StemsegClusterParams* p, const int32_t* n_points_dev, int64_t* labels,
+                                       int32_t* primary, void* meta, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
     SS_REQUIRE(p != nullptr, "seq_cluster: null params");
     SS_REQUIRE(p->n_points >= 1 && p->n_points < 0x7FFFFFFFll, "seq_cluster: n_points %lld out of range",
                static_cast<long long>(p->n_points));
@@ -326,6 +332,7 @@ extern "C" int32_t stemseg_seq_cluster(const float* embeddings, const float* ban
 
     ClusterArgs a;
     a.emb = embeddings; a.bw = bandwidths; a.seed = seediness;
+    a.n_dev = n_points_dev;
     a.n = p->n_points;
     a.v = p->embedding_dims - p->n_free_dims;
     for (int k = 0; k < kMaxE; ++k) a.free_bw[k] = k < p->n_free_dims ? p->free_dim_bandwidths[k] : 0.f;

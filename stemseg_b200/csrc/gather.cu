@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(kThreads) fg_write_kernel(const Src mask, long
 
 __global__ void __launch_bounds__(256) fg_gather_kernel(const float* __restrict__ src, long long channel_stride,
                                                         int channels, const int* __restrict__ indices, long long n,
-                                                        int transform, float* __restrict__ dst) {
+                                                        const int* __restrict__ n_dev, int transform,
+                                                        float* __restrict__ dst) {
     const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (n_dev != nullptr && *n_dev < n) n = *n_dev;        // device-side count (no host round trip)
     if (p >= n) return;
     const long long idx = indices[p];
     for (int c = 0; c < channels; ++c) {
@@ -192,15 +194,15 @@ extern "C" int32_t stemseg_fg_compact_threshold(const float* values, float thres
 }
 
 extern "C" int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, int32_t channels,
-                                     const int32_t* indices, int64_t n, int32_t transform, float* dst,
-                                     void* stream_) {
+                                     const int32_t* indices, int64_t n, const int32_t* n_dev, int32_t transform,
+                                     float* dst, void* stream_) {
     SS_REQUIRE(transform == 0 || transform == 1, "fg_gather: transform must be 0 (none) or 1 (exp*10)");
     SS_REQUIRE(channels >= 1, "fg_gather: channels must be >= 1");
     if (n == 0) return STEMSEG_OK;
     SS_REQUIRE(src && indices && dst && n > 0, "fg_gather: bad arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-    fg_gather_kernel<<<blocks, 256, 0, stream>>>(src, channel_stride, channels, indices, n, transform, dst);
+    fg_gather_kernel<<<blocks, 256, 0, stream>>>(src, channel_stride, channels, indices, n, n_dev, transform, dst);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

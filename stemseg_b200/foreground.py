@@ -17,10 +17,37 @@ class ForegroundIndex(object):
     ``coord_list()`` reproduces the reference's list(T) of (y, x) index tuples (online_chainer.py:11-22).
     """
 
-    def __init__(self, indices, frame_counts, shape):
-        self.indices = indices
-        self.frame_counts = frame_counts
+    def __init__(self, indices, frame_counts, shape, counts_dev=None):
+        self._indices = indices              # device int32; capacity T*H*W while the counts are still on the device
+        self._frame_counts = frame_counts    # python list, or None until `resolve()` fetched counts_dev
         self.shape = tuple(shape)
+        self.counts_dev = counts_dev         # device int32 [T+1] (per-frame counts, then the total) or None
+
+    def resolve(self):
+        """Fetch the counts from the device (one sync) if that has not happened yet."""
+        if self._frame_counts is None:
+            counts = self.counts_dev.cpu().tolist()
+            self._frame_counts = counts[:-1]
+            self._indices = self._indices[:counts[-1]]
+        return self
+
+    @property
+    def indices(self):
+        return self.resolve()._indices
+
+    @property
+    def frame_counts(self):
+        return self.resolve()._frame_counts
+
+    @property
+    def capacity_indices(self):
+        """Index buffer without forcing a sync (valid entries: the first counts_dev[-1])."""
+        return self._indices
+
+    @property
+    def total_dev(self):
+        """Device pointer holder of the total count, or None when the count is already known on the host."""
+        return None if self._frame_counts is not None else self.counts_dev[-1:]
 
     @property
     def num_points(self):
@@ -51,7 +78,7 @@ class ForegroundIndex(object):
 
 
 @torch.no_grad()
-def compact_foreground(masks, threshold=None):
+def compact_foreground(masks, threshold=None, sync=True):
     """masks: [T,H,W] tensor on a CUDA device, any integer/bool dtype (non-zero = foreground).
 
     With ``threshold`` given, ``masks`` is an fp32 map and foreground = ``masks > threshold`` evaluated inside the
@@ -86,6 +113,8 @@ def compact_foreground(masks, threshold=None):
         else:
             _lib.check(lib.stemseg_fg_compact(_lib.ptr(m), t, h * w, _lib.ptr(indices), _lib.ptr(counts),
                                               _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        if not sync:     # counts stay on the device: gather / clustering read them there (no host round trip)
+            return ForegroundIndex(indices, None, (t, h, w), counts_dev=counts)
         counts_host = counts.cpu().tolist()          # one sync (the reference syncs once per frame)
     return ForegroundIndex(indices[:counts_host[-1]], counts_host[:-1], (t, h, w))
 
@@ -103,12 +132,14 @@ def gather_points(channel_first_map, fg_index, transform="none"):
     inner = x.shape[1] * x.shape[2] * x.shape[3]
     if not x[0].is_contiguous() or (c > 1 and x.stride(0) < inner):
         x = x.contiguous()
-    n = fg_index.num_points
+    total_dev = fg_index.total_dev
+    idx = fg_index.capacity_indices
+    n = int(idx.shape[0])            # capacity when the count is still on the device
     out = torch.empty((n, c), dtype=torch.float32, device=x.device)
     if n == 0:
         return out
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c,
-                                         _lib.ptr(fg_index.indices), n, code, _lib.ptr(out), _lib.stream_ptr()))
+        _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c, _lib.ptr(idx), n,
+                                         _lib.ptr(total_dev), code, _lib.ptr(out), _lib.stream_ptr()))
     return out

@@ -30,6 +30,7 @@ class SubclipPipeline(object):
         if seediness_head is None and embedding_head.seediness_channels == 0:
             raise ValueError("no seediness source: give a seediness head or an embedding head with seediness_output")
         self.fuse_heads = True          # run all heads as one HeadSet (shared im2col operand, one CUDA graph)
+        self.use_step_graph = True      # heads + compaction + gather + clustering replayed as one CUDA graph
         self._group = None
         self._group_key = None
 
@@ -96,8 +97,104 @@ class SubclipPipeline(object):
         assert labels.numel() == emb_flat.shape[0]                     # online_chainer.py:286
         return labels, meta, fg
 
+    # ---- whole step as ONE CUDA graph ---------------------------------------------------------------------------
+    def _capture_step(self, emb_in, fg_mask):
+        """heads plan -> compaction -> gathers -> clustering captured into one CUDA graph.  Point counts stay on the
+        device (compaction writes them, gather / clustering read them), so nothing inside needs the host."""
+        from stemseg_b200 import decoder as D
+        group = self._head_group()
+        dev = emb_in[0].device
+        e, v = self.embedding_head.embedding_size, self.embedding_head.variance_channels
+        in_planes = [D.pack_activation(f, group.planes) for f in emb_in]
+        mask_static = None if fg_mask is None else torch.empty_like(fg_mask)
+        if mask_static is not None:
+            mask_static.copy_(fg_mask)
+
+        def body(streams):
+            outs = [o.squeeze(0) for o in group._plan(in_planes, streams=streams)]
+            out = outs.pop(0)
+            seediness = out[e + v:e + v + 1] if self.embedding_head.seediness_channels else outs.pop(0)
+            semseg = outs.pop(0) if self.semseg_head is not None else None
+            emb, var = out[:e], out[e:e + v]
+            if mask_static is not None:
+                fg = compact_foreground(mask_static, sync=False)
+            elif semseg is not None and self.semseg_head.has_foreground_channel:
+                fg = compact_foreground(semseg[-1], threshold=0.0, sync=False)
+            else:
+                fg = compact_foreground(seediness[0], threshold=self.seediness_fg_threshold, sync=False)
+            ef = gather_points(emb, fg)
+            bf = gather_points(var, fg, transform="exp10")
+            sf = gather_points(seediness, fg)
+            pending = self.clusterer.launch(ef, bf, sf.reshape(-1), 1, n_points_dev=fg.total_dev)
+            return {"emb": emb, "var": var, "seed": seediness, "semseg": semseg, "fg": fg, "pending": pending,
+                    "flat": (ef, bf, sf)}
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            D.KEEP = []
+            body(None)
+            D.KEEP = []
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        from stemseg_b200 import _lib
+        D.KEEP = []
+        before = _lib.KERNEL_LAUNCHES[0]
+        with torch.cuda.graph(graph):
+            state = body(streams)
+        kernels = _lib.KERNEL_LAUNCHES[0] - before
+        keep, D.KEEP = D.KEEP, []
+        return {"graph": graph, "in_planes": in_planes, "mask": mask_static, "state": state, "keep": keep,
+                "kernels": kernels, "streams": streams, "planes": group.planes}
+
+    @torch.no_grad()
+    def run_graphed(self, features, fg_mask=None, cluster_label_start=1):
+        """Same result as __call__, replaying one captured CUDA graph per step (inputs packed into static planes)."""
+        from stemseg_b200 import _lib, decoder as D
+        emb_in = [features[s] for s in self.embedding_scales]
+        if emb_in[0].shape[0] != 1:
+            raise ValueError("SubclipPipeline processes one sub-clip at a time (batch dimension must be 1)")
+        dev = emb_in[0].device
+        key = (tuple(tuple(f.shape) for f in emb_in), str(dev),
+               None if fg_mask is None else (tuple(fg_mask.shape), fg_mask.dtype),
+               tuple(id(sp) for sp in self._head_group().specs))
+        if not hasattr(self, "_step_graphs"):
+            self._step_graphs = {}
+        with torch.cuda.device(dev):
+            entry = self._step_graphs.get(key)
+            if entry is None:
+                entry = self._step_graphs[key] = self._capture_step(emb_in, fg_mask)
+            for f, pl in zip(emb_in, entry["in_planes"]):
+                D.pack_activation(f, entry["planes"], out=pl)
+            if fg_mask is not None:
+                entry["mask"].copy_(fg_mask)
+            entry["graph"].replay()
+            _lib.KERNEL_LAUNCHES[0] += entry["kernels"]
+            st = entry["state"]
+            fg = st["fg"]
+            counts = fg.counts_dev.to("cpu", non_blocking=False).tolist()        # sync #1 (small)
+            pending = dict(st["pending"])
+            pending["label_start"] = int(cluster_label_start)
+            labels, meta = self.clusterer.finish(pending)
+            labels = labels.clone()
+            if cluster_label_start != 1:          # labels are offset-invariant (SURVEY §8a quirk v)
+                labels = torch.where(labels >= 0, labels + (cluster_label_start - 1), labels)
+        from stemseg_b200.foreground import ForegroundIndex
+        res = SubclipResult()
+        res.embeddings, res.variances, res.seediness = st["emb"].clone(), st["var"].clone(), st["seed"].clone()
+        res.semseg_logits = None if st["semseg"] is None else st["semseg"].clone()
+        res.labels, res.meta = labels, meta
+        res.fg_index = ForegroundIndex(fg.capacity_indices[:counts[-1]].clone(), counts[:-1], fg.shape)
+        res.frame_labels = list(labels.split(counts[:-1], 0))
+        return res
+
     @torch.no_grad()
     def __call__(self, features, fg_mask=None, cluster_label_start=1):
+        if self.use_step_graph and self.fuse_heads and tuple(self.embedding_scales) == (32, 16, 8, 4) and \
+                self.embedding_head.use_cuda_graph:
+            return self.run_graphed(features, fg_mask, cluster_label_start)
         res = SubclipResult()
         res.embeddings, res.variances, res.seediness, res.semseg_logits = self.run_heads(features)
         if fg_mask is None and res.semseg_logits is not None and self.semseg_head.has_foreground_channel:

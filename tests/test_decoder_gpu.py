@@ -222,3 +222,37 @@ def test_fused_head_epilogue_matches_unfused(name, cuda_device):
     for _, sl in output_groups(case, fused.shape[1]).items():
         a, b = fused[:, sl].double(), unfused[:, sl].double()
         assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()
+
+
+def test_whole_step_graph_matches_eager(cuda_device):
+    """One captured graph (heads + compaction + gather + clustering, device-side point count) == eager calls."""
+    from stemseg_b200.pipeline import build_davis_pipeline
+    pipe = build_davis_pipeline(cuda_device, num_frames=8, in_channels=64, inter_channels=(64, 64, 32, 32))
+    rng = np.random.default_rng(0)
+    for trial, (h4, w4) in enumerate(((24, 40), (24, 40), (32, 24))):
+        feats_list = do.seeded_features(50 + trial, 1, 64, 8, h4, w4)
+        feats = {s: f.to(cuda_device) for s, f in zip((32, 16, 8, 4), feats_list)}
+        mask = torch.from_numpy(rng.random((8, h4, w4)) < 0.6).to(cuda_device)
+        for fg_mask, start in ((None, 1), (mask, 1), (mask, 12)):
+            pipe.use_step_graph = True
+            a = pipe(feats, fg_mask=fg_mask, cluster_label_start=start)
+            a2 = pipe(feats, fg_mask=fg_mask, cluster_label_start=start)
+            pipe.use_step_graph = False
+            b = pipe(feats, fg_mask=fg_mask, cluster_label_start=start)
+            assert torch.equal(a.labels, b.labels) and torch.equal(a.labels, a2.labels)
+            assert a.meta == b.meta
+            assert a.fg_index.frame_counts == b.fg_index.frame_counts
+            assert torch.equal(a.fg_index.indices, b.fg_index.indices)
+            assert torch.equal(a.embeddings, b.embeddings) and torch.equal(a.seediness, b.seediness)
+            assert [x.numel() for x in a.frame_labels] == [x.numel() for x in b.frame_labels]
+
+
+def test_step_graph_empty_foreground(cuda_device):
+    from stemseg_b200.pipeline import build_davis_pipeline
+    pipe = build_davis_pipeline(cuda_device, num_frames=8, in_channels=64, inter_channels=(64, 64, 32, 32))
+    feats_list = do.seeded_features(7, 1, 64, 8, 24, 32)
+    feats = {s: f.to(cuda_device) for s, f in zip((32, 16, 8, 4), feats_list)}
+    mask = torch.zeros((8, 24, 32), dtype=torch.uint8, device=cuda_device)
+    res = pipe(feats, fg_mask=mask)
+    assert res.labels.numel() == 0 and res.meta["instance_labels"] == []
+    assert res.fg_index.frame_counts == [0] * 8

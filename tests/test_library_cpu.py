@@ -50,7 +50,7 @@ def test_invalid_arguments_are_reported(lib):
     params = _lib.StemsegClusterParams()
     params.n_points = 0
     params.embedding_dims = 4
-    rc = lib.stemseg_seq_cluster(None, None, None, params, None, None, None, None, 0, None)
+    rc = lib.stemseg_seq_cluster(None, None, None, params, None, None, None, None, None, 0, None)
     assert rc == -1
     assert b"n_points" in lib.stemseg_last_error()
     params.max_instances = 1000
