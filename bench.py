@@ -249,10 +249,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     # per-launch durations of the tcgen05 conv kernel: the same plan launched eagerly (the timed region replays it
     # as a CUDA graph, where individual launches cannot be bracketed), CUDA events on the launching stream
     group = pipe._head_group()
-    group.use_graph = False
+    group.use_graph, pipe.use_step_graph = False, False
     step_resident()
     _, conv_events = timed(step_resident, args.steps, profile=True)
-    group.use_graph = True
+    group.use_graph, pipe.use_step_graph = True, True
 
     # per-stage breakdown (untimed extra pass on rank 0; informational)
     stages = {}
