@@ -169,7 +169,11 @@ int32_t stemseg_conv3d_auto_split(const StemsegConvShape* shape);
 /* out[n][t][h][w][cout] (fp32) = conv(act) + bias.  tcgen05 implicit GEMM, TMA im2col, fp32 accumulation in TMEM.
  * max_ctas > 0 caps the persistent grid (used to run independent branches concurrently on separate streams). */
 int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias, float* out,
-                                   const StemsegConvShape* shape, int32_t max_ctas, void* stream);
+                                   float* stat_partial, const StemsegConvShape* shape, int32_t max_ctas, void* stream);
+/* stat_partial (optional, split_k == 1 only): [n][cout][tiles][2] per-tile (sum, sum of squares) of every output
+ * channel, written by the conv epilogue from the accumulator registers; tiles = stemseg_conv3d_tiles_per_sample().
+ * stemseg_group_norm_finalize turns it into the GroupNorm affine table without re-reading the conv output. */
+int32_t stemseg_conv3d_tiles_per_sample(const StemsegConvShape* shape);
 
 /* GroupNorm statistics of an NDHWC fp32 tensor -> per-channel affine table scale_shift[n][c][2] with
  *   scale = rstd * gamma, shift = beta - mean * rstd * gamma   (biased variance, eps inside the sqrt; nn.GroupNorm(32, C),
@@ -181,6 +185,13 @@ size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c)
 int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_t slices, int32_t n, int64_t spatial, int32_t c,
                                  int32_t channels_per_group, float eps, const float* gamma, const float* beta,
                                  float* scale_shift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Second half of stemseg_group_norm_stats for partial sums produced elsewhere (the conv epilogue): `partial` points
+ * at channel 0 of the c channels to normalise inside a [n][c_total][chunks][2] buffer, partial_sample_stride =
+ * c_total*chunks*2 floats. */
+int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample_stride, int32_t chunks, int32_t n,
+                                    int64_t spatial, int32_t c, int32_t channels_per_group, float eps,
+                                    const float* gamma, const float* beta, float* scale_shift, void* stream);
 
 /* relu(x * scale + shift) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
  * (embedding_decoder.py:22-24; common.py:8-24).  scale_shift NULL = no normalisation (NormType Identity). */

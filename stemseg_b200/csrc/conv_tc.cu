@@ -44,6 +44,9 @@ struct ConvTcParams {
     float* out;                // [k_slices][n][t][h][w][cout] fp32 (partial sums when k_slices > 1)
     const float* bias;         // [cout] or nullptr
     int num_stages;            // smem pipeline depth
+    float* stat_partial;       // optional [n][cout][tiles_per_sample][2]: per-tile (sum, sum of squares) of every output
+                               // channel, consumed by gn_finalize (GroupNorm statistics without re-reading the output)
+    int tiles_per_sample;
     // ---- epilogue mode 1: fused output heads (the accumulator row never leaves the SM) ----------------------
     //   out[n][j][t][h][w] = act_j( W_out[j] . acc_row + up(p_low)[j] + b_j ) + coord_j
     int epi_mode;              // 0 = fp32 NDHWC store (+bias), 1 = output heads
@@ -171,6 +174,21 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            (static_cast<uint32_t>(kBlockM >> 4) << 24);
 }
 
+// Column sums over the 32 rows held by a warp: v[i] is this lane's (row's) value of column i.  Butterfly
+// reduce-scatter (31 shuffles instead of 160): afterwards v[0] of lane l is the sum of column l over the 32 lanes.
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+}
+
 template <int BLOCK_N>
 constexpr int tmem_columns() {
     return kAccStages * BLOCK_N <= 32 ? 32 : kAccStages * BLOCK_N <= 64 ? 64 : kAccStages * BLOCK_N <= 128 ? 128
@@ -225,7 +243,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
-    float* s_head_w = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);    // [J][BLOCK_N] then [J] bias
+    float* s_stat = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);      // [4 quarters][BLOCK_N][2]
+    float* s_head_w = s_stat + 4 * BLOCK_N * 2;                                        // [J][BLOCK_N] then [J] bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -354,25 +373,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                                  ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
                                   static_cast<size_t>(tc.n_tile) * BLOCK_N);
                 const float* bias = (p.bias && tc.slice == 0) ? p.bias + tc.n_tile * BLOCK_N : nullptr;
+                const bool stats = p.stat_partial != nullptr;
+                if (stats) asm volatile("bar.sync 1, %0;" ::"n"(kNumEpilogueThreads) : "memory");  // s_stat free again
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + c, v);
                     tmem_ld_wait();
-                    if (valid) {
+                    float f[32];
 #pragma unroll
-                        for (int q = 0; q < 32; q += 4) {
-                            float4 o;
-                            o.x = __uint_as_float(v[q + 0]);
-                            o.y = __uint_as_float(v[q + 1]);
-                            o.z = __uint_as_float(v[q + 2]);
-                            o.w = __uint_as_float(v[q + 3]);
-                            if (bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
-                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                            }
-                            *reinterpret_cast<float4*>(out_row + c + q) = o;
+                    for (int q = 0; q < 32; q += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[q + 0]);
+                        o.y = __uint_as_float(v[q + 1]);
+                        o.z = __uint_as_float(v[q + 2]);
+                        o.w = __uint_as_float(v[q + 3]);
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
+                        if (valid) *reinterpret_cast<float4*>(out_row + c + q) = o;
+                        f[q + 0] = valid ? o.x : 0.f;
+                        f[q + 1] = valid ? o.y : 0.f;
+                        f[q + 2] = valid ? o.z : 0.f;
+                        f[q + 3] = valid ? o.w : 0.f;
+                    }
+                    if (stats) {
+                        float f2[32];
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) f2[q] = f[q] * f[q];
+                        warp_column_sums(f, lane);
+                        warp_column_sums(f2, lane);
+                        s_stat[(quarter * BLOCK_N + c + lane) * 2 + 0] = f[0];
+                        s_stat[(quarter * BLOCK_N + c + lane) * 2 + 1] = f2[0];
+                    }
+                }
+                if (stats) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(kNumEpilogueThreads) : "memory");
+                    const int et = threadIdx.x - (kNumThreads - kNumEpilogueThreads);
+                    const int m_in_sample = (tile / (p.k_slices * p.n_tiles_n)) % p.tiles_per_sample;
+                    for (int col = et; col < BLOCK_N; col += kNumEpilogueThreads) {
+                        float a = 0.f, b = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {        // fixed order: deterministic
+                            a += s_stat[(qq * BLOCK_N + col) * 2 + 0];
+                            b += s_stat[(qq * BLOCK_N + col) * 2 + 1];
+                        }
+                        float* dstp = p.stat_partial +
+                                      ((static_cast<size_t>(tc.n) * p.cout + tc.n_tile * BLOCK_N + col) * p.tiles_per_sample +
+                                       m_in_sample) * 2;
+                        dstp[0] = a;
+                        dstp[1] = b;
                     }
                 }
             } else {
@@ -517,8 +568,9 @@ template <int BLOCK_N, int BLOCK_K, int PLANES>
 int launch_variant(const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaStream_t stream) {
     constexpr int stage = stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
     const int head_bytes = p.epi_mode == 1 ? static_cast<int>(align_up((p.head_j * BLOCK_N + p.head_j) * sizeof(float), 16)) : 0;
-    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + head_bytes;
-    int stages = (kSmemBudget - head_bytes) / stage;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * BLOCK_N * 2 * 4 /*stat staging*/ + head_bytes;
+    int stages = (kSmemBudget - head_bytes - 4 * BLOCK_N * 2 * 4) / stage;
+    if (stages * stage + fixed > kSmemLimit) stages = (kSmemLimit - fixed) / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2 || stages * stage + fixed > kSmemLimit) {
         set_error("conv_tc: tile %dx%dx%d does not fit shared memory with %d head outputs", BLOCK_N, BLOCK_K, PLANES,
@@ -595,7 +647,8 @@ extern "C" int32_t stemseg_conv3d_auto_split(const StemsegConvShape* s) {
 }
 
 static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, const float* bias, float* out,
-                           const StemsegConvShape* s, int32_t max_ctas, void* stream_, const ConvTcParams* head) {
+                           float* stat_partial, const StemsegConvShape* s, int32_t max_ctas, void* stream_,
+                           const ConvTcParams* head) {
     SS_REQUIRE(s != nullptr && act_planes && weight_planes && (out || head), "conv3d: null pointer");
     SS_REQUIRE(s->planes == 1 || s->planes == 2, "conv3d: planes must be 1 or 2");
     SS_REQUIRE(s->kernel_size == 3 || s->kernel_size == 1, "conv3d: kernel_size must be 1 or 3");
@@ -629,6 +682,10 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     p.out = out;
     p.bias = bias;
     p.num_stages = 0;
+    p.tiles_per_sample = p.tiles_t * p.tiles_h * p.tiles_w;
+    p.stat_partial = stat_partial;
+    SS_REQUIRE(stat_partial == nullptr || (p.k_slices == 1 && head == nullptr),
+               "conv3d: fused statistics need an unsplit plain-store launch");
     p.epi_mode = 0;
     p.head_j = 0;
     if (head != nullptr) {
@@ -666,9 +723,16 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
 }
 
 extern "C" int32_t stemseg_conv3d_bf16_planes(const void* act_planes, const void* weight_planes, const float* bias,
-                                              float* out, const StemsegConvShape* s, int32_t max_ctas,
-                                              void* stream_) {
-    return conv3d_impl(act_planes, weight_planes, bias, out, s, max_ctas, stream_, nullptr);
+                                              float* out, float* stat_partial, const StemsegConvShape* s,
+                                              int32_t max_ctas, void* stream_) {
+    return conv3d_impl(act_planes, weight_planes, bias, out, stat_partial, s, max_ctas, stream_, nullptr);
+}
+
+extern "C" int32_t stemseg_conv3d_tiles_per_sample(const StemsegConvShape* s) {
+    if (s == nullptr || s->t < 1 || s->h < 1 || s->w < 1) return 0;
+    int tt, th, tw;
+    choose_box(s->t, s->h, s->w, &tt, &th, &tw);
+    return ((s->t + tt - 1) / tt) * ((s->h + th - 1) / th) * ((s->w + tw - 1) / tw);
 }
 
 extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const void* weight_planes,
@@ -690,5 +754,5 @@ extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const voi
     head.y_abs = fmaxf(1.0f, static_cast<float>(static_cast<double>(s->h) / static_cast<double>(s->w)));
     head.t_abs = time_scale;
     head.head_out = out;
-    return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, s, max_ctas, stream_, &head);
+    return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, nullptr, s, max_ctas, stream_, &head);
 }

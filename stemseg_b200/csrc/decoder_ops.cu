@@ -106,7 +106,7 @@ __device__ __forceinline__ float4 load_sum_slices(const float4* p, size_t slice_
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(float* __restrict__ x, long long spatial, int c,
                                                          int row_stride, int slices, size_t slice_stride, int chunk_voxels,
-                                                         float* __restrict__ partial /*[n][chunks][c][2]*/,
+                                                         float* __restrict__ partial /*[n][c][chunks][2]*/,
                                                          int chunks) {
     extern __shared__ float s_acc[];                 // [rows][c][2]
     const int quads = c / 4;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(float* __restrict__ x, 
             a += s_acc[(rr * c + ch) * 2 + 0];
             b += s_acc[(rr * c + ch) * 2 + 1];
         }
-        float* out = partial + ((static_cast<size_t>(n) * chunks + chunk) * c + ch) * 2;
+        float* out = partial + ((static_cast<size_t>(n) * c + ch) * chunks + chunk) * 2;   // [n][c][chunks][2]
         out[0] = a;
         out[1] = b;
     }
@@ -157,17 +157,18 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(float* __restrict__ x, 
 
 // one block per (group, sample): mean / rstd of the group and the per-channel affine table
 //   scale[ch] = rstd * gamma[ch],  shift[ch] = beta[ch] - mean * rstd * gamma[ch]
-__global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restrict__ partial, int chunks, int c,
-                                                          int cpg, long long spatial, float eps,
+__global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restrict__ partial, size_t sample_stride,
+                                                          int chunks, int c, int cpg, long long spatial, float eps,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ scale_shift /*[n][c][2]*/) {
     const int g = blockIdx.x, n = blockIdx.y;
     double s = 0.0, ss = 0.0;
+    // the cpg channels of a group are contiguous in the [n][c][chunks][2] layout: one coalesced stream
+    const float2* base = reinterpret_cast<const float2*>(partial + n * sample_stride) + static_cast<size_t>(g) * cpg * chunks;
     for (int i = threadIdx.x; i < chunks * cpg; i += blockDim.x) {
-        const int chunk = i / cpg, ch = g * cpg + i % cpg;
-        const float* p = partial + ((static_cast<size_t>(n) * chunks + chunk) * c + ch) * 2;
-        s += p[0];
-        ss += p[1];
+        const float2 v = __ldg(base + i);
+        s += v.x;
+        ss += v.y;
     }
     __shared__ double sh[2][512];
     sh[0][threadIdx.x] = s;
@@ -255,6 +256,42 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
         }
         const size_t off = ((((static_cast<size_t>(nn) * t_out + to) * h + hh) * w + ww) * c) + 4 * q;
         store_planes4(dst, plane_elems, planes, off, acc);
+    }
+}
+
+// flat variant of gn_relu_pool_kernel<false> for row_stride == c and one slice (the big 4x layer): no index
+// decomposition, two independent 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256) gn_relu_flat_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
+                                                           long long quads_per_sample, int quads, long long total_quads,
+                                                           __nv_bfloat16* __restrict__ dst, size_t plane_elems, int planes) {
+    const long long stride = 1ll * gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i0 < total_quads; i0 += 2 * stride) {
+        const long long i1 = i0 + stride;
+        const bool has1 = i1 < total_quads;
+        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x) + i0);
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has1) a1 = __ldcs(reinterpret_cast<const float4*>(x) + i1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            const long long i = u == 0 ? i0 : i1;
+            const float4 a = u == 0 ? a0 : a1;
+            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (scale_shift) {
+                const long long nn = i / quads_per_sample;
+                const int q = static_cast<int>(i % quads);
+                const float4* tab = reinterpret_cast<const float4*>(scale_shift) + (nn * quads + q) * 2;
+                const float4 t0 = __ldg(tab), t1 = __ldg(tab + 1);
+                sc[0] = t0.x; sh[0] = t0.y; sc[1] = t0.z; sh[1] = t0.w;
+                sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
+            }
+            float r[4];
+            r[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
+            r[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+            r[2] = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
+            r[3] = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+            store_planes4(dst, plane_elems, planes, static_cast<size_t>(i) * 4, r);
+        }
     }
 }
 
@@ -518,7 +555,25 @@ extern "C" int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_
                                                                   static_cast<size_t>(n) * spatial * row_stride,
                                                                   chunk_voxels, static_cast<float*>(workspace), chunks);
     gn_finalize_kernel<<<dim3(c / channels_per_group, n), 512, 0, stream>>>(
-        static_cast<const float*>(workspace), chunks, c, channels_per_group, spatial, eps, gamma, beta, scale_shift);
+        static_cast<const float*>(workspace), static_cast<size_t>(c) * chunks * 2, chunks, c, channels_per_group,
+        spatial, eps, gamma, beta, scale_shift);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample_stride, int32_t chunks,
+                                               int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
+                                               float eps, const float* gamma, const float* beta, float* scale_shift,
+                                               void* stream_) {
+    SS_REQUIRE(partial && gamma && beta && scale_shift, "group_norm_finalize: null pointer");
+    SS_REQUIRE(n >= 1 && spatial >= 1 && chunks >= 1 && c >= 1, "group_norm_finalize: bad shape");
+    SS_REQUIRE(channels_per_group >= 1 && channels_per_group <= 512 && c % channels_per_group == 0,
+               "group_norm_finalize: bad group size");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 7) == 0, "group_norm_finalize: partial must be 8-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    gn_finalize_kernel<<<dim3(c / channels_per_group, n), 512, 0, stream>>>(
+        partial, static_cast<size_t>(partial_sample_stride), chunks, c, channels_per_group, spatial, eps, gamma, beta,
+        scale_shift);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
@@ -542,6 +597,9 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
+    else if (row_stride == c && slices == 1)
+        gn_relu_flat_kernel<<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
+            x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, total, dst, plane_elems, planes);
     else
         gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);

@@ -107,7 +107,7 @@ def pack_activation(x, planes, out=None):
     return Planes(dst, n, t, h, w, c)
 
 
-def conv3d(act, packed, max_ctas=0, allow_split=False):
+def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False):
     """Planes x PackedConv -> fp32 NDHWC tensor [n,t,h,w,cout] (tcgen05 implicit GEMM).
 
     With allow_split the library may split the taps over several CTAs for layers with fewer tiles than SMs; the
@@ -119,29 +119,36 @@ def conv3d(act, packed, max_ctas=0, allow_split=False):
         raise ValueError("activation / weight precision mismatch")
     shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes,
                                   1)
+    stat = None
     with torch.cuda.device(act.tensor.device):
         if allow_split:
             shape.split_k = lib.stemseg_conv3d_auto_split(shape)
+        if allow_split and shape.split_k > 1:
             out = torch.empty((shape.split_k, act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
                               device=act.tensor.device)
         else:
             out = torch.empty((act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
                               device=act.tensor.device)
+            if want_stats:     # per-tile channel sums straight from the accumulators (GroupNorm statistics)
+                tiles = lib.stemseg_conv3d_tiles_per_sample(shape)
+                stat = torch.empty((act.n, packed.cout, tiles, 2), dtype=torch.float32, device=act.tensor.device)
         ev = None
         if PROFILE_EVENTS is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _check(lib.stemseg_conv3d_bf16_planes(_lib.ptr(act.tensor), _lib.ptr(packed.planes_tensor),
-                                              _lib.ptr(packed.bias), _lib.ptr(out), shape, max_ctas,
+                                              _lib.ptr(packed.bias), _lib.ptr(out), _lib.ptr(stat), shape, max_ctas,
                                               _lib.stream_ptr()))
         if ev is not None:
             ev[1].record()
             PROFILE_EVENTS.append(((act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size,
                                     act.planes), ev[0], ev[1]))
+    if want_stats:
+        return out, stat
     return out
 
 
-def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None):
+def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None, stat=None):
     """fp32 NDHWC conv output ([split_k,] n,t,h,w,c_total) -> relu(GN(y)) [-> avgpool] as Planes.
 
     gamma None = no normalisation.  channel_slice=(c0, c) normalises channels [c0, c0+c) of a wider (multi-head)
@@ -157,13 +164,21 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
         if gamma is not None:
             if c % num_groups != 0:
                 raise ValueError("channels %d not divisible by %d groups" % (c, num_groups))
-            ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             scale_shift = torch.empty((n, c, 2), dtype=torch.float32, device=dev)
-            _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, c // num_groups, float(eps),
-                                                _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift), _lib.ptr(ws),
-                                                ws_bytes, _lib.stream_ptr()))
-            KEEP.extend((ws, scale_shift))
+            if stat is not None:          # statistics came out of the conv epilogue: finalize only
+                chunks = stat.shape[2]
+                part_ptr = _lib.c_void_p(stat.data_ptr() + 4 * c0 * chunks * 2)
+                _check(lib.stemseg_group_norm_finalize(part_ptr, c_total * chunks * 2, chunks, n, t * h * w, c,
+                                                       c // num_groups, float(eps), _lib.ptr(gamma), _lib.ptr(beta),
+                                                       _lib.ptr(scale_shift), _lib.stream_ptr()))
+                KEEP.append(scale_shift)
+            else:
+                ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, c // num_groups,
+                                                    float(eps), _lib.ptr(gamma), _lib.ptr(beta),
+                                                    _lib.ptr(scale_shift), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+                KEEP.extend((ws, scale_shift))
             slices = 1                               # the statistics pass summed the split-K slices into slice 0
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
@@ -304,6 +319,7 @@ class HeadSet(object):
         self.planes = planes
         self.use_graph = use_graph
         self.fuse_output_heads = True       # conv_4 merge GEMM + output heads in one kernel (epilogue fusion)
+        self.fuse_stats = True              # GroupNorm statistics from the conv epilogue (unsplit layers)
         self.pools, self.tscale = pool_schedule(num_frames)
         self.first_stage = {}
         for name, _ in BLOCKS:
@@ -313,8 +329,8 @@ class HeadSet(object):
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
     def _branch(self, name, n_stages, a_in, trace):
         """All conv stages of one scale block for every head; returns per-head Planes."""
-        y = conv3d(a_in, self.first_stage[name], allow_split=True)
-        KEEP.append(y)
+        y, stat = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats)
+        KEEP.extend((y, stat))
         outs, c0 = [], 0
         for hi, spec in enumerate(self.specs):
             conv, gamma, beta = spec.weights.stages[name][0]
@@ -323,16 +339,17 @@ class HeadSet(object):
                 trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
             a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
                                      self.pools[0] and name != "block_4x", self.planes,
-                                     channel_slice=(c0, conv.cout))
+                                     channel_slice=(c0, conv.cout), stat=stat)
             KEEP.append(a.tensor)
             c0 += conv.cout
             for j in range(1, n_stages):
                 conv, gamma, beta = spec.weights.stages[name][j]
-                yj = conv3d(a, conv, allow_split=True)
-                KEEP.append(yj)
+                yj, statj = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats)
+                KEEP.extend((yj, statj))
                 if trace is not None and hi == trace[0]:
                     trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj.clone()
-                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j], self.planes)
+                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j], self.planes,
+                                         stat=statj)
                 KEEP.append(a.tensor)
             outs.append(a)
         return outs

@@ -256,3 +256,20 @@ def test_step_graph_empty_foreground(cuda_device):
     res = pipe(feats, fg_mask=mask)
     assert res.labels.numel() == 0 and res.meta["instance_labels"] == []
     assert res.fg_index.frame_counts == [0] * 8
+
+
+def test_epilogue_statistics_match_stats_kernel(cuda_device):
+    """GroupNorm statistics from the conv epilogue (per-tile channel sums) == the standalone statistics kernel."""
+    name = "emb_fullwidth_t8"
+    sd, feats, case = dc.build_case(name)
+    head = build_head(case, sd, cuda_device)
+    dev = [f.to(cuda_device) for f in feats]
+    with torch.no_grad():
+        a = head(dev)
+        hs = head._get_head_set()
+        hs.fuse_stats = False
+        hs._entries.clear()
+        b = head(dev)
+    for _, sl in output_groups(case, a.shape[1]).items():
+        x, y = a[:, sl].double(), b[:, sl].double()
+        assert (x - y).abs().max().item() <= 5e-6 * y.abs().max().item()
