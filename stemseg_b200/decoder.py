@@ -329,7 +329,8 @@ class HeadSet(object):
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
     def _branch(self, name, n_stages, a_in, trace):
         """All conv stages of one scale block for every head; returns per-head Planes."""
-        y, stat = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats)
+        res = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats)
+        y, stat = res if self.fuse_stats else (res, None)
         KEEP.extend((y, stat))
         outs, c0 = [], 0
         for hi, spec in enumerate(self.specs):
@@ -344,7 +345,8 @@ class HeadSet(object):
             c0 += conv.cout
             for j in range(1, n_stages):
                 conv, gamma, beta = spec.weights.stages[name][j]
-                yj, statj = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats)
+                res = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats)
+                yj, statj = res if self.fuse_stats else (res, None)
                 KEEP.extend((yj, statj))
                 if trace is not None and hi == trace[0]:
                     trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj.clone()
