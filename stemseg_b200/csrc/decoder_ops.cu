@@ -262,15 +262,17 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
 // flat variant of gn_relu_pool_kernel<false> for row_stride == c and one slice (the big 4x layer): no index
 // decomposition, two independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256) gn_relu_flat_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
-                                                           long long quads_per_sample, int quads, long long total_quads,
-                                                           __nv_bfloat16* __restrict__ dst, size_t plane_elems, int planes) {
+                                                           long long quads_per_sample, int quads, int row_quads,
+                                                           long long total_quads, __nv_bfloat16* __restrict__ dst,
+                                                           size_t plane_elems, int planes) {
     const long long stride = 1ll * gridDim.x * blockDim.x;
     for (long long i0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i0 < total_quads; i0 += 2 * stride) {
         const long long i1 = i0 + stride;
         const bool has1 = i1 < total_quads;
-        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x) + i0);
+        // source rows may be wider than the normalised slice (channel slice of a multi-head conv output)
+        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x) + (i0 / quads) * row_quads + (i0 % quads));
         float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has1) a1 = __ldcs(reinterpret_cast<const float4*>(x) + i1);
+        if (has1) a1 = __ldcs(reinterpret_cast<const float4*>(x) + (i1 / quads) * row_quads + (i1 % quads));
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !has1) break;
@@ -597,9 +599,9 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
-    else if (row_stride == c && slices == 1)
+    else if (slices == 1)
         gn_relu_flat_kernel<<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
-            x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, total, dst, plane_elems, planes);
+            x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, row_stride / 4, total, dst, plane_elems, planes);
     else
         gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
