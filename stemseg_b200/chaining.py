@@ -1,0 +1,230 @@
+"""Sub-clip chaining: windows over a video, per-sub-clip clustering on the device, and the sequential stitch.
+
+Host-side mirror of the reference's inference glue around the hot path (same names / arguments / return structure):
+  * ``get_subsequence_frames``           stemseg/inference/main.py:23-49
+  * ``TrackContainer``                   stemseg/inference/online_chainer.py:25-117
+  * ``OnlineChainer.process`` / ``cluster_subsequence`` / ``associate_clusters``   online_chainer.py:120-343
+The per-point work of ``cluster_subsequence`` (gather + clustering) runs in the CUDA kernels; the stitch
+(``stitch_subsequences``) is integer host logic on label vectors: a K1 x K2 (<= 20 x 20) IoU table from one joint
+histogram per overlap and scipy's Hungarian solver, exactly like online_chainer.py:291-343.  It only consumes
+labels, which is what makes sub-clips independent and the path clip-parallel (stemseg_b200/parallel.py).
+"""
+from collections import defaultdict
+
+import numpy as np
+import torch
+from scipy.optimize import linear_sum_assignment
+
+from stemseg_b200.foreground import ForegroundIndex, compact_foreground, gather_points
+
+DEFAULT_FRAME_OVERLAP = {"davis": 6, "ytvis": 4, "kittimots": 4}      # defaults.yaml:91,101,110
+
+
+def get_subsequence_frames(seq_len, subseq_len, dataset_name=None, frame_overlap=-1):
+    """Overlapping windows of a video (main.py:23-49).  Returns (list of frame-index lists, padded-frame flags|None)."""
+    if frame_overlap <= 0:
+        if dataset_name not in DEFAULT_FRAME_OVERLAP:
+            raise NotImplementedError()
+        frame_overlap = DEFAULT_FRAME_OVERLAP[dataset_name]
+    assert frame_overlap < subseq_len
+    if seq_len < subseq_len:                           # short video: repeat frame 0 (main.py:37-39)
+        pad = subseq_len - seq_len
+        return [[0] * pad + list(range(seq_len))], [True] * pad + [False] * seq_len
+    windows, last = [], -1
+    for t in range(0, seq_len - subseq_len + 1, subseq_len - frame_overlap):
+        windows.append(list(range(t, t + subseq_len)))
+        last = windows[-1][-1]
+    if last != seq_len - 1:                            # tail window (main.py:46-47)
+        windows.append(list(range(seq_len - subseq_len, seq_len)))
+    return windows, None
+
+
+class TrackContainer(object):
+    """Final stitched labels of every frame (online_chainer.py:25-117)."""
+
+    def __init__(self, num_frames):
+        self._frame_labels = [None for _ in range(num_frames)]
+        self._is_frozen = [False for _ in range(num_frames)]
+        self._highest_instance_id = 0
+
+    def add_labels(self, frame_nums, labels):
+        assert all([self._frame_labels[t] is None for t in frame_nums])
+        for t, labels_t in zip(frame_nums, labels):
+            self._frame_labels[t] = labels_t
+            if labels_t.numel() > 0:
+                self._highest_instance_id = max(self._highest_instance_id, labels_t.max().item())
+        return self._highest_instance_id + 1
+
+    def labels_exist(self, frame_num):
+        return self._frame_labels[frame_num] is not None
+
+    def has_fg_pixels(self, frame_num):
+        assert self.labels_exist(frame_num)
+        return self._frame_labels[frame_num].numel() > 0
+
+    def get_labels(self, frame_nums):
+        assert all(self.labels_exist(t) for t in frame_nums)
+        return [self._frame_labels[t] for t in frame_nums]
+
+    def update_labels(self, frame_num, labels):
+        assert self.labels_exist(frame_num)
+        assert not self._is_frozen[frame_num]
+        self._frame_labels[frame_num] = labels
+        if labels.numel() > 0:
+            self._highest_instance_id = max(self._highest_instance_id, labels.max().item())
+        return self._highest_instance_id
+
+    def freeze_frame(self, frame_num):
+        assert self.labels_exist(frame_num)
+        self._is_frozen[frame_num] = True
+
+    def get_track_mask_idxes(self):
+        """-> (per-frame label tensors, {id: point count}, {id: lifetime})  (online_chainer.py:94-117)."""
+        counts = defaultdict(lambda: 0)
+        span = defaultdict(lambda: [10000, -1])
+        for frame_num, labels in enumerate(self._frame_labels):
+            ids, cnt = np.unique(labels.numpy(), return_counts=True)
+            for i, c in zip(ids.tolist(), cnt.tolist()):
+                counts[i] += c
+                span[i][0] = min(frame_num, span[i][0])
+                span[i][1] = max(frame_num, span[i][1])
+        lifetimes = {k: v[1] - v[0] for k, v in span.items()}
+        return self._frame_labels, counts, lifetimes
+
+
+OUTLIER_LABEL = -1
+
+
+def associate_label_sets(labels_1, labels_2):
+    """IoU association of the clusters of two labelings of the same points (online_chainer.py:291-343).
+
+    labels_*: 1-D integer arrays (np or torch).  Returns (associations [(l1, l2)], unassigned_1, unassigned_2,
+    costs of the chosen pairs, (recall matrix, unique_1, unique_2)) like the reference."""
+    a = labels_1.cpu().numpy() if torch.is_tensor(labels_1) else np.asarray(labels_1)
+    b = labels_2.cpu().numpy() if torch.is_tensor(labels_2) else np.asarray(labels_2)
+    assert a.shape == b.shape, "Shape mismatch: {}, {}".format(a.shape, b.shape)
+    # the reference builds the label lists through python sets (online_chainer.py:307-308); keep its ordering
+    unique_1 = list(set(np.unique(a).tolist()) - {OUTLIER_LABEL})
+    unique_2 = list(set(np.unique(b).tolist()) - {OUTLIER_LABEL})
+    assert not set(unique_1).intersection(set(unique_2)), "Labels overlap: {}, {}".format(unique_1, unique_2)
+    costs = np.zeros((len(unique_1), len(unique_2)), np.float32)
+    recall = np.zeros((len(unique_1), len(unique_2)), np.float32)
+    if unique_1 and unique_2:
+        pos1 = {l: i for i, l in enumerate(unique_1)}
+        pos2 = {l: i for i, l in enumerate(unique_2)}
+        i1 = np.array([pos1.get(v, -1) for v in a.tolist()], np.int64) if a.size < 64 else \
+            np.vectorize(lambda v: pos1.get(v, -1), otypes=[np.int64])(a)
+        i2 = np.array([pos2.get(v, -1) for v in b.tolist()], np.int64) if b.size < 64 else \
+            np.vectorize(lambda v: pos2.get(v, -1), otypes=[np.int64])(b)
+        n1, n2 = len(unique_1), len(unique_2)
+        both = (i1 >= 0) & (i2 >= 0)
+        inter = np.bincount(i1[both] * n2 + i2[both], minlength=n1 * n2).reshape(n1, n2)     # joint histogram
+        size1 = np.bincount(i1[i1 >= 0], minlength=n1)
+        size2 = np.bincount(i2[i2 >= 0], minlength=n2)
+        union = size1[:, None] + size2[None, :] - inter
+        iou = inter.astype(np.float32) / union.astype(np.float32)          # fp32 division like the torch ops
+        costs = (1.0 - iou.astype(np.float64)).astype(np.float32)          # 1. - iou.item() stored as fp32
+        recall = inter.astype(np.float32) / size1.astype(np.float32)[:, None]
+    rows, cols = linear_sum_assignment(costs)                              # online_chainer.py:330
+    associations = []
+    un1, un2 = set(unique_1), set(unique_2)
+    for r, c in zip(rows, cols):
+        associations.append((unique_1[r], unique_2[c]))
+        un1.remove(unique_1[r])
+        un2.remove(unique_2[c])
+    return associations, un1, un2, costs[rows, cols], (recall, unique_1, unique_2)
+
+
+def stitch_subsequences(num_frames, subseq_frames, subseq_local_labels, subseq_meta=None):
+    """The sequential stitch of OnlineChainer.process (online_chainer.py:162-236) on per-sub-clip LOCAL labels.
+
+    subseq_local_labels[i]: list (one int64 CPU tensor per frame of sub-clip i) of cluster labels obtained with
+    cluster_label_start=1.  Clustering is label-offset invariant, so adding ``next_track_label - 1`` reproduces what the
+    reference gets by clustering sub-clip i with cluster_label_start=next_track_label (online_chainer.py:183-185).
+    Returns (TrackContainer, list of per-sub-clip relabelled label lists, list of meta dicts)."""
+    container = TrackContainer(num_frames)
+    next_track_label = 1
+    out_labels, out_meta = [], []
+    for i, frames in enumerate(subseq_frames):
+        offset = next_track_label - 1
+        labels = [torch.where(l >= 0, l + offset, l) for l in subseq_local_labels[i]]
+        meta = None
+        if subseq_meta is not None:
+            meta = dict(subseq_meta[i])
+            meta['instance_labels'] = [l + offset for l in meta['instance_labels']]
+        if i == 0:
+            next_track_label = container.add_labels(frames, labels)
+            out_labels.append(labels)
+            out_meta.append(meta)
+            continue
+        prev = subseq_frames[i - 1]
+        overlapping = sorted(list(set(frames).intersection(set(prev))))
+        existing = container.get_labels(overlapping)
+        current = [labels[j] for j, t in enumerate(frames) if t in overlapping]
+        associations, _, _, _, _ = associate_label_sets(torch.cat(existing), torch.cat(current))
+        for j, t in enumerate(frames):
+            if t in overlapping:
+                continue
+            for associated_label, current_label in associations:
+                labels[j] = torch.where(labels[j] == current_label, torch.tensor(associated_label).to(labels[j]),
+                                        labels[j])
+            next_track_label = container.add_labels([t], [labels[j]])
+        if meta is not None:
+            for associated_label, current_label in associations:
+                idx = meta['instance_labels'].index(current_label)
+                meta['instance_labels'][idx] = associated_label
+        out_labels.append(labels)
+        out_meta.append(meta)
+    return container, out_labels, out_meta
+
+
+class OnlineChainer(object):
+    """Drop-in for stemseg.inference.online_chainer.OnlineChainer with the per-point work on the device."""
+    OUTLIER_LABEL = OUTLIER_LABEL
+
+    def __init__(self, clusterer, embedding_resize_factor):
+        self.clusterer = clusterer
+        self.resize_scale = embedding_resize_factor
+        if embedding_resize_factor != 1.0:
+            raise NotImplementedError("embedding_resize_factor != 1.0 (full-resolution clustering, online_chainer.py:"
+                                      "128-140) is a 'next' row (SURVEY.md §8f-4)")
+
+    @torch.no_grad()
+    def cluster_subsequence(self, mask_idxes, embeddings, bandwidths, seediness, label_start, return_fg_embeddings):
+        """mask_idxes: ForegroundIndex of the sub-clip's frames (see ``process``); maps are [C,T,H,W] CUDA tensors.
+        Returns (per-frame label list, [N,E] foreground embeddings, clustering meta) (online_chainer.py:244-289)."""
+        assert len(mask_idxes.frame_counts) == embeddings.shape[1]
+        emb_flat = gather_points(embeddings, mask_idxes)
+        bw_flat = gather_points(bandwidths, mask_idxes)
+        seed_flat = gather_points(seediness, mask_idxes)
+        labels, meta = self.clusterer(emb_flat, bandwidths=bw_flat, seediness=seed_flat,
+                                      cluster_label_start=label_start, return_label_masks=return_fg_embeddings)
+        assert labels.numel() == emb_flat.shape[0]
+        return list(labels.split(mask_idxes.frame_counts, 0)), emb_flat, meta
+
+    @torch.no_grad()
+    def process(self, masks, subsequences, return_fg_embeddings=False):
+        """masks [T,H,W]; subsequences: list of dicts with 'frames', 'embeddings' [E,T',H,W], 'bandwidths' (already
+        activated), 'seediness'.  Same return tuple as the reference (online_chainer.py:241-242)."""
+        device = self.clusterer.device
+        num_frames = masks.shape[0]
+        fg_all = compact_foreground(masks.to(device))
+        mask_idxes = fg_all.coord_list()
+        frames_list, local_labels, metas, fg_embeddings = [], [], [], []
+        for subseq in subsequences:
+            if isinstance(subseq['frames'], dict):
+                subseq['frames'] = sorted(subseq['frames'].keys())
+            frames = list(subseq['frames'])
+            emb = subseq['embeddings'].to(device)
+            assert emb.shape[-2:] == masks.shape[-2:], \
+                "Size mismatch between embeddings {} and masks {}".format(emb.shape, masks.shape)
+            labels, fg_emb, meta = self.cluster_subsequence(
+                fg_all.frame_slice(frames), emb, subseq['bandwidths'].to(device), subseq['seediness'].to(device), 1,
+                return_fg_embeddings)
+            frames_list.append(frames)
+            local_labels.append([l.cpu() for l in labels])
+            metas.append(meta)
+            if return_fg_embeddings:
+                fg_embeddings.append(fg_emb.cpu())
+        container, subseq_labels_list, meta_out = stitch_subsequences(num_frames, frames_list, local_labels, metas)
+        return container.get_track_mask_idxes(), mask_idxes, subseq_labels_list, fg_embeddings, meta_out

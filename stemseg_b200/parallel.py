@@ -1,0 +1,94 @@
+"""Clip-parallel inference: the path shards at sub-clip granularity.
+
+Sub-clips are independent through heads -> gather -> clustering (the only cross-clip state of the reference is
+``cluster_label_start``, online_chainer.py:162,183-196, and clustering is label-offset invariant), so sub-clip i is
+processed by rank ``i % world_size`` with local labels 1..K_i.  ONE exchange step follows: an all-gather of the
+per-frame label vectors (+ counts, + the small clustering metadata); every rank then replays the same sequential
+stitch (stemseg_b200.chaining.stitch_subsequences) and obtains bit-identical global track ids.  Backend: NCCL over
+NVLink on the GPU box (device tensors), gloo in the CPU tests; payload < 1 MB per sub-clip, so stock all_gather is the
+right tool (no custom transport).
+"""
+import torch
+import torch.distributed as dist
+
+from stemseg_b200.chaining import stitch_subsequences
+
+
+def shard_subclips(num_subclips, rank, world_size):
+    """Round-robin ownership: sub-clip i -> rank i % world_size."""
+    return [i for i in range(num_subclips) if i % world_size == rank]
+
+
+def exchange_and_stitch(num_frames, subseq_frames, local_results, group=None, device=None):
+    """All-gather the per-sub-clip labels of every rank, then stitch.
+
+    subseq_frames: frame lists of ALL sub-clips (every rank knows the windowing).
+    local_results: {sub-clip index: (list of per-frame int64 label tensors (local labels, start 1), meta dict)} for
+    the sub-clips this rank owns.  Returns (TrackContainer, relabelled per-sub-clip labels, metas) on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_sub = len(subseq_frames)
+    if world == 1:
+        labels = [[l.cpu() for l in local_results[i][0]] for i in range(n_sub)]
+        return stitch_subsequences(num_frames, subseq_frames, labels, [local_results[i][1] for i in range(n_sub)])
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+            else torch.device("cpu")
+    owned = shard_subclips(n_sub, rank, world)
+    assert sorted(local_results.keys()) == owned, "rank %d owns %s but got %s" % (rank, owned, sorted(local_results))
+    max_local = (n_sub + world - 1) // world
+    max_t = max(len(f) for f in subseq_frames)
+    # 1) per-frame counts of every owned sub-clip (fixed shape -> plain all_gather)
+    counts = torch.full((max_local, max_t), -1, dtype=torch.int64)
+    for slot, i in enumerate(owned):
+        for j, lab in enumerate(local_results[i][0]):
+            counts[slot, j] = lab.numel()
+    counts = counts.to(device)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = [c.cpu() for c in all_counts]
+    totals = [int(c.clamp(min=0).sum()) for c in all_counts]
+    # 2) labels, padded to the largest per-rank total
+    pad_to = max(max(totals), 1)
+    flat = [lab.reshape(-1).to(torch.int32) for i in owned for lab in local_results[i][0]]
+    mine = torch.cat(flat) if flat else torch.zeros(0, dtype=torch.int32)
+    buf = torch.full((pad_to,), -2, dtype=torch.int32, device=device)
+    buf[:mine.numel()] = mine.to(device)
+    all_labels = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(all_labels, buf, group=group)
+    # 3) clustering metadata (tiny python dicts)
+    metas_mine = {i: local_results[i][1] for i in owned}
+    all_metas = [None] * world
+    dist.all_gather_object(all_metas, metas_mine, group=group)
+    # reassemble in sub-clip order
+    labels_by_clip, meta_by_clip = {}, {}
+    for r in range(world):
+        cursor = 0
+        lab_r = all_labels[r].cpu().to(torch.int64)
+        for slot, i in enumerate(shard_subclips(n_sub, r, world)):
+            per_frame = []
+            for j in range(len(subseq_frames[i])):
+                c = int(all_counts[r][slot, j])
+                per_frame.append(lab_r[cursor:cursor + c].clone())
+                cursor += c
+            labels_by_clip[i] = per_frame
+            meta_by_clip[i] = all_metas[r][i]
+    return stitch_subsequences(num_frames, subseq_frames, [labels_by_clip[i] for i in range(n_sub)],
+                               [meta_by_clip[i] for i in range(n_sub)])
+
+
+@torch.no_grad()
+def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, group=None):
+    """Run the owned sub-clips through ``pipeline`` (stemseg_b200.pipeline.SubclipPipeline) and stitch globally.
+
+    masks: [T,h,w] foreground masks of the whole video (or None -> per-sub-clip seediness threshold);
+    features_for_clip(i) -> {scale: tensor} pyramid of sub-clip i (only called for owned sub-clips)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    local = {}
+    for i in shard_subclips(len(subseq_frames), rank, world):
+        fg_mask = None if masks is None else masks[subseq_frames[i]]
+        res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
+        local[i] = ([l.cpu() for l in res.frame_labels], res.meta)
+    num_frames = max(max(f) for f in subseq_frames) + 1
+    return exchange_and_stitch(num_frames, subseq_frames, local, group=group)
