@@ -201,9 +201,16 @@ def run_gpu_arm(args, rank, local_rank, world):
     def step_resident():
         return pipe(dev_feats, fg_mask=fg_mask)
 
+    from stemseg_b200.pipeline import HostFeatureStream
+    stager = HostFeatureStream(device)
+    e2e_state = {"ticket": None}
+
     def step_e2e():
-        feats = {s: f.to(device, non_blocking=True) for s, f in host_feats.items()}
-        res = pipe(feats, fg_mask=fg_mask)
+        # public API with HOST buffers: pinned pyramid -> (double-buffered H2D) -> pipeline -> labels back on the host
+        ticket = e2e_state["ticket"] if e2e_state["ticket"] is not None else stager.submit(host_feats)
+        e2e_state["ticket"] = stager.submit(host_feats)          # prefetch the next clip while this one computes
+        res = pipe(stager.get(ticket), fg_mask=fg_mask)
+        stager.release(ticket)
         return res.labels.cpu()
 
     def barrier():
@@ -341,7 +348,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         "grid_points_per_sec": value * GRID_POINTS,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "pinned host pyramid, double-buffered H2D on a copy stream (clip i+1 uploads while clip i "
+                        "computes; one extra clip is uploaded per run), labels copied back to the host every step"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -214,6 +214,48 @@ class SubclipPipeline(object):
         return res
 
 
+class HostFeatureStream(object):
+    """Double-buffered host -> device staging of feature pyramids held in pinned host memory.
+
+    ``submit`` enqueues the copies of one pyramid on a dedicated copy stream and returns a ticket; ``get`` makes the
+    current (compute) stream wait for them; ``release`` tells the stager the compute stream is done reading the
+    buffer.  The H2D transfer of clip i+1 (282 MB at 480p) thereby overlaps the kernels of clip i."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._buffers = [None] * depth
+        self._ready = [None] * depth
+        self._free = [None] * depth
+        self._next = 0
+
+    def submit(self, host_features):
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        if self._buffers[slot] is None or any(self._buffers[slot][k].shape != v.shape for k, v in host_features.items()):
+            self._buffers[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                                   for k, v in host_features.items()}
+        with torch.cuda.stream(self.copy_stream):
+            if self._free[slot] is not None:
+                self.copy_stream.wait_event(self._free[slot])      # previous consumer of this buffer has finished
+            for k, v in host_features.items():
+                self._buffers[slot][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._ready[slot] = ev
+        return slot
+
+    def get(self, ticket):
+        torch.cuda.current_stream(self.device).wait_event(self._ready[ticket])
+        return self._buffers[ticket]
+
+    def release(self, ticket):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[ticket] = ev
+
+
 def build_davis_pipeline(device, num_frames=8, precision="fp32", in_channels=256,
                          inter_channels=(256, 256, 128, 128), min_seediness_prob=0.0, seed=42):
     """Random-init model of the shipped DAVIS config (davis_1.yaml: E=4 'xyff', separate seediness head, GN32,
