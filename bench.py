@@ -80,15 +80,31 @@ def cpu_reference_step(feats, emb_sd, seed_sd):
     return labels, meta
 
 
+def best_cpu_threads(feats, emb_sd, seed_sd):
+    """The reference's torch-CPU convs do not scale to every core of a big host: time one clip at a few thread
+    counts and keep the fastest (this is the most favourable setting for the CPU baseline)."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    best, best_t = ncpu, None
+    for threads in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 16)}, reverse=True):
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        cpu_reference_step(feats, emb_sd, seed_sd)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = threads, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     feats = make_features_cpu()
     emb_sd, seed_sd = build_cpu_reference()
-    for _ in range(args.warmup):
+    threads = best_cpu_threads(feats, emb_sd, seed_sd)
+    for _ in range(max(0, args.warmup - 1)):
         cpu_reference_step(feats, emb_sd, seed_sd)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -179,6 +195,43 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def cluster_fullres_roofline(device, peaks, n=T * HP * WP, e=4, iters=5):
+    """SequentialClustering at full resolution (--resize_embeddings, inference/main.py:242-243): the working set
+    (80 MB) no longer fits comfortably next to everything else and the kernel is bandwidth-bound.
+    Algorithmic bytes = N*(4E+12)*(K+1)  (SURVEY.md §8d)."""
+    import numpy as np
+    import torch
+    from stemseg_b200.clusterers import SequentialClustering
+    rng = np.random.default_rng(0)
+    centres = rng.uniform(-1, 1, size=(24, e)).astype(np.float32)
+    which = rng.integers(0, 24, size=n)
+    emb = torch.from_numpy(centres[which] + 0.05 * rng.standard_normal((n, e)).astype(np.float32)).to(device)
+    bw = torch.full((n, e - 2), 100.0, device=device)
+    seed = torch.rand(n, 1, device=device)
+    clusterer = SequentialClustering(0.5, 0.3, 0.0, 2, [0.3, 0.3], device)
+    pend = clusterer.launch(emb, bw, seed.reshape(-1), 1)
+    _, meta = clusterer.finish(pend)
+    k = len(meta["instance_labels"])
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        a.record()
+        pend = clusterer.launch(emb, bw, seed.reshape(-1), 1)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = sorted(times)[len(times) // 2]
+    bytes_alg = n * (4 * e + 12) * (k + 1)
+    achieved = bytes_alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "seq_cluster_kernel<4> N=%d K=%d" % (n, k),
+            "launch_ms": ms, "algorithmic_mb_per_launch": bytes_alg / 1e6,
+            "peak_source": "%s hbm_gbs" % peaks["source"],
+            "note": "working set 80 MB < 126 MB L2: part of the traffic is served by L2, so this can exceed the DRAM "
+                    "copy peak"}
+
+
 def run_gpu_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -253,14 +306,6 @@ def run_gpu_arm(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps)
 
-    # per-launch durations of the tcgen05 conv kernel: the same plan launched eagerly (the timed region replays it
-    # as a CUDA graph, where individual launches cannot be bracketed), CUDA events on the launching stream
-    group = pipe._head_group()
-    group.use_graph, pipe.use_step_graph = False, False
-    step_resident()
-    _, conv_events = timed(step_resident, args.steps, profile=True)
-    group.use_graph, pipe.use_step_graph = True, True
-
     # per-stage breakdown (untimed extra pass on rank 0; informational)
     stages = {}
     if rank == 0:
@@ -275,6 +320,19 @@ def run_gpu_arm(args, rank, local_rank, world):
             return a.elapsed_time(b) / reps, out
         stages["heads_ms"], (emb, var, seedi, _) = ev_time(lambda: pipe.run_heads(dev_feats))
         stages["gather_cluster_ms"], _ = ev_time(lambda: pipe.cluster(emb, var, seedi, fg_mask))
+
+    # secondary roofline: the clustering kernel in its HBM-bound regime (full-resolution point set, N = 3 317 760)
+    cluster_roofline = None
+    if rank == 0:
+        cluster_roofline = cluster_fullres_roofline(device, load_peaks())
+
+    # per-launch durations of the tcgen05 conv kernel: the same plan launched eagerly (the timed region replays it
+    # as a CUDA graph, where individual launches cannot be bracketed), CUDA events on the launching stream
+    group = pipe._head_group()
+    group.use_graph, pipe.use_step_graph = False, False
+    step_resident()
+    _, conv_events = timed(step_resident, args.steps, profile=True)
+    group.use_graph, pipe.use_step_graph = True, True
 
     if rank != 0:
         if world > 1:
@@ -317,19 +375,17 @@ def run_gpu_arm(args, rank, local_rank, world):
     # CPU baseline on a bounded sample (rank 0, N == 1 only)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
         cfeats = make_features_cpu()
         emb_sd, seed_sd = build_cpu_reference()
-        cpu_reference_step(cfeats, emb_sd, seed_sd)
+        threads = best_cpu_threads(cfeats, emb_sd, seed_sd)
         reps, t0 = 0, time.perf_counter()
         while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 20):
             cpu_reference_step(cfeats, emb_sd, seed_sd)
             reps += 1
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": reps / dt, "unit": "clips/s", "cores": threads, "kind": "port",
-                        "sample": "%d full clips after 1 warm-up (oracle port: torch-CPU fp32 heads + numpy gather/"
-                                  "clustering, all host threads)" % reps}
+                        "sample": "%d full clips after warm-up (oracle port: torch-CPU fp32 heads + numpy gather/"
+                                  "clustering; fastest of {all, 1/2, 1/4, 16} host threads)" % reps}
 
     h2d = sum(f.numel() * f.element_size() for f in host_feats.values())
     d2h = GRID_POINTS * 8
@@ -353,6 +409,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                         "computes; one extra clip is uploaded per run), labels copied back to the host every step"},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_cluster_fullres": cluster_roofline,
         "cpu_baseline": cpu_baseline,
         "stages": stages,
     }

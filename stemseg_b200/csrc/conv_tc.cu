@@ -628,11 +628,18 @@ int auto_split(const StemsegConvShape* s) {
     const long long tiles = 1ll * s->n * ((s->t + tt - 1) / tt) * ((s->h + th - 1) / th) * ((s->w + tw - 1) / tw) *
                             (s->cout / block_n_for(s->cout));
     const int sms = device_sm_count();
-    if (tiles >= sms) return 1;
+    // cost model: rounds of CTAs x (fraction of the K loop per CTA + fixed per-tile overhead ~4 % of a full tile)
     int best = 1;
-    const int options[3] = {3, 9, 27};
-    for (int o : options)
-        if (tiles * o <= 2ll * sms) best = o;
+    double best_cost = 1e30;
+    const int options[4] = {1, 3, 9, 27};
+    for (int o : options) {
+        const long long rounds = (tiles * o + sms - 1) / sms;
+        const double cost = static_cast<double>(rounds) * (1.0 / o + 0.04) + (o > 1 ? 0.05 : 0.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = o;
+        }
+    }
     return best;
 }
 
