@@ -143,11 +143,13 @@ class SequentialClustering(ClustererBase):
                 "workspace": workspace}
 
     @torch.no_grad()
-    def finish(self, pending, return_label_masks=False):
-        """Fetch the metadata of a launched clustering (the one device->host sync) and format the reference's dict."""
+    def finish(self, pending, return_label_masks=False, meta_host=None):
+        """Fetch the metadata of a launched clustering (the one device->host sync) and format the reference's dict.
+        ``meta_host``: the metadata words already copied to the host by the caller (asynchronous pipelines)."""
         labels, primary, e = pending["labels"], pending["primary"], pending["e"]
         cluster_label_start = pending["label_start"]
-        meta_host = pending["meta"].cpu()
+        if meta_host is None:
+            meta_host = pending["meta"].cpu()
         n_done = int(meta_host[2])
         labels, primary = labels[:n_done], primary[:n_done]
         self._last_primary = primary

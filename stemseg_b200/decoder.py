@@ -372,8 +372,7 @@ class HeadSet(object):
                     branches[b] = self._branch(name, n_stages, in_planes[b], trace)
             for b in range(3):
                 main.wait_event(streams[b].record_event())
-        outputs = []
-        for hi, spec in enumerate(self.specs):
+        def merge_chain(hi, spec):
             x = branches[0][hi]
             out = None
             for k in range(3):
@@ -390,7 +389,25 @@ class HeadSet(object):
                     KEEP.append(x.tensor)
                 else:
                     out = head_output(z, y_low, self.tscale[k], spec.out_spec)
-            outputs.append(out)
+            return out
+
+        outputs = [None] * len(self.specs)
+        if streams is None or len(self.specs) == 1:
+            for hi, spec in enumerate(self.specs):
+                outputs[hi] = merge_chain(hi, spec)
+        else:
+            # the heads' merge chains are independent: head 0 on the main stream, the others on side streams
+            fork = main.record_event()
+            used = []
+            for hi, spec in enumerate(self.specs):
+                st = main if hi == 0 else streams[(hi - 1) % len(streams)]
+                if st is not main:
+                    st.wait_event(fork)
+                    used.append(st)
+                with torch.cuda.stream(st):
+                    outputs[hi] = merge_chain(hi, spec)
+            for st in used:
+                main.wait_event(st.record_event())
         return outputs
 
     # ---- entry point -------------------------------------------------------------------------------------------

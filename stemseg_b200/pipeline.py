@@ -14,7 +14,45 @@ from stemseg_b200.foreground import compact_foreground, gather_points
 
 
 class SubclipResult(object):
-    __slots__ = ("labels", "frame_labels", "meta", "fg_index", "embeddings", "variances", "seediness", "semseg_logits")
+    __slots__ = ("labels", "frame_labels", "meta", "fg_index", "embeddings", "variances", "seediness", "semseg_logits",
+                 "labels_host")
+
+
+class PendingStep(object):
+    """A sub-clip whose GPU work has been enqueued (SubclipPipeline.submit)."""
+
+    def __init__(self, pipe, state, snap, counts_host, meta_host, labels_host, done, label_start):
+        self._pipe, self._state, self._snap = pipe, state, snap
+        self._counts_host, self._meta_host, self._labels_host = counts_host, meta_host, labels_host
+        self._done, self._label_start = done, label_start
+        self._result = None
+
+    def result(self):
+        if self._result is not None:
+            return self._result
+        from stemseg_b200.foreground import ForegroundIndex
+        self._done.synchronize()                       # this step only
+        counts = self._counts_host.tolist()
+        pending = dict(self._state["pending"])
+        pending["labels"], pending["primary"] = self._snap["labels"], self._snap["primary"]
+        pending["label_start"] = self._label_start
+        labels, meta = self._pipe.clusterer.finish(pending, meta_host=self._meta_host)
+        if self._label_start != 1:                     # labels are offset-invariant (SURVEY §8a quirk v)
+            labels = torch.where(labels >= 0, labels + (self._label_start - 1), labels)
+        res = SubclipResult()
+        res.embeddings, res.variances, res.seediness = self._snap["emb"], self._snap["var"], self._snap["seed"]
+        res.semseg_logits = self._snap["semseg"]
+        res.labels, res.meta = labels, meta
+        res.fg_index = ForegroundIndex(self._snap["indices"][:counts[-1]], counts[:-1], self._state["fg"].shape)
+        res.frame_labels = list(labels.split(counts[:-1], 0))
+        res.labels_host = None
+        if self._labels_host is not None:
+            host = self._labels_host[:counts[-1]]
+            if self._label_start != 1:
+                host = torch.where(host >= 0, host + (self._label_start - 1), host)
+            res.labels_host = host
+        self._result = res
+        return res
 
 
 class SubclipPipeline(object):
@@ -150,8 +188,12 @@ class SubclipPipeline(object):
                 "kernels": kernels, "streams": streams, "planes": group.planes}
 
     @torch.no_grad()
-    def run_graphed(self, features, fg_mask=None, cluster_label_start=1):
-        """Same result as __call__, replaying one captured CUDA graph per step (inputs packed into static planes)."""
+    def submit(self, features, fg_mask=None, cluster_label_start=1, labels_to_host=False):
+        """Enqueue one sub-clip (pack -> graph replay -> stream-ordered copies of the results) and return at once.
+
+        The returned ``PendingStep.result()`` synchronises on that step only, so the host work of step i (and the
+        pack / replay of step i+1) overlaps the kernels of step i: ``submit`` the next clip before asking for the
+        previous result."""
         from stemseg_b200 import _lib, decoder as D
         emb_in = [features[s] for s in self.embedding_scales]
         if emb_in[0].shape[0] != 1:
@@ -173,22 +215,26 @@ class SubclipPipeline(object):
             entry["graph"].replay()
             _lib.KERNEL_LAUNCHES[0] += entry["kernels"]
             st = entry["state"]
-            fg = st["fg"]
-            counts = fg.counts_dev.to("cpu", non_blocking=False).tolist()        # sync #1 (small)
-            pending = dict(st["pending"])
-            pending["label_start"] = int(cluster_label_start)
-            labels, meta = self.clusterer.finish(pending)
-            labels = labels.clone()
-            if cluster_label_start != 1:          # labels are offset-invariant (SURVEY §8a quirk v)
-                labels = torch.where(labels >= 0, labels + (cluster_label_start - 1), labels)
-        from stemseg_b200.foreground import ForegroundIndex
-        res = SubclipResult()
-        res.embeddings, res.variances, res.seediness = st["emb"].clone(), st["var"].clone(), st["seed"].clone()
-        res.semseg_logits = None if st["semseg"] is None else st["semseg"].clone()
-        res.labels, res.meta = labels, meta
-        res.fg_index = ForegroundIndex(fg.capacity_indices[:counts[-1]].clone(), counts[:-1], fg.shape)
-        res.frame_labels = list(labels.split(counts[:-1], 0))
-        return res
+            # stream-ordered snapshots: the next replay may overwrite the graph's static buffers right after these
+            snap = {"labels": st["pending"]["labels"].clone(), "primary": st["pending"]["primary"].clone(),
+                    "indices": st["fg"].capacity_indices.clone(), "emb": st["emb"].clone(), "var": st["var"].clone(),
+                    "seed": st["seed"].clone(), "semseg": None if st["semseg"] is None else st["semseg"].clone()}
+            counts_host = torch.empty(st["fg"].counts_dev.shape, dtype=torch.int32, pin_memory=True)
+            meta_host = torch.empty(st["pending"]["meta"].shape, dtype=torch.int32, pin_memory=True)
+            counts_host.copy_(st["fg"].counts_dev, non_blocking=True)
+            meta_host.copy_(st["pending"]["meta"], non_blocking=True)
+            labels_host = None
+            if labels_to_host:
+                labels_host = torch.empty(snap["labels"].shape, dtype=torch.int64, pin_memory=True)
+                labels_host.copy_(snap["labels"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+        return PendingStep(self, st, snap, counts_host, meta_host, labels_host, done, int(cluster_label_start))
+
+    @torch.no_grad()
+    def run_graphed(self, features, fg_mask=None, cluster_label_start=1):
+        """Same result as the eager path, replaying one captured CUDA graph per step."""
+        return self.submit(features, fg_mask, cluster_label_start).result()
 
     @torch.no_grad()
     def __call__(self, features, fg_mask=None, cluster_label_start=1):

@@ -273,3 +273,26 @@ def test_epilogue_statistics_match_stats_kernel(cuda_device):
     for _, sl in output_groups(case, a.shape[1]).items():
         x, y = a[:, sl].double(), b[:, sl].double()
         assert (x - y).abs().max().item() <= 5e-6 * y.abs().max().item()
+
+
+def test_submit_result_pipelining(cuda_device):
+    """submit()/result(): results of consecutive different clips stay correct when collected one step late."""
+    from stemseg_b200.pipeline import build_davis_pipeline
+    pipe = build_davis_pipeline(cuda_device, num_frames=8, in_channels=64, inter_channels=(64, 64, 32, 32))
+    clips = []
+    for k in range(4):
+        fl = do.seeded_features(200 + k, 1, 64, 8, 24, 32)
+        clips.append({s: f.to(cuda_device) for s, f in zip((32, 16, 8, 4), fl)})
+    sync = [pipe(c) for c in clips]
+    pend, got = None, []
+    for c in clips:
+        nxt = pipe.submit(c, labels_to_host=True)
+        if pend is not None:
+            got.append(pend.result())
+        pend = nxt
+    got.append(pend.result())
+    for a, b in zip(sync, got):
+        assert torch.equal(a.labels, b.labels) and a.meta == b.meta
+        assert torch.equal(a.embeddings, b.embeddings)
+        assert torch.equal(b.labels_host, b.labels.cpu())
+        assert a.fg_index.frame_counts == b.fg_index.frame_counts
