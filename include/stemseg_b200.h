@@ -161,6 +161,9 @@ typedef struct StemsegConvShape {
     int32_t split_k;         /* 1, or 3 / 9 / 27 (kernel_size 3): number of tap slices computed by separate CTAs;
                                 out then holds split_k partial sums [split_k][n][t][h][w][cout] (bias in slice 0)
                                 which the GroupNorm kernels add in a fixed order                                  */
+    int32_t tiles_per_cta;   /* 0: persistent CTAs (one per SM) looping over the tiles; > 0: short-lived CTAs that own
+                                this many consecutive tiles -- lets higher-priority kernels of concurrent branches
+                                obtain SMs while a long layer runs                                                */
 } StemsegConvShape;
 
 /* Split that fills the SMs for a latency-bound (few-tile) layer on the current device; 1 for large layers. */

@@ -17,14 +17,19 @@ mask = torch.ones((bench.T, bench.H4, bench.W4), dtype=torch.uint8, device=devic
 for _ in range(4):
     pipe(feats, fg_mask=mask)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for _ in range(2):
-        pipe(feats, fg_mask=mask)
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    pend = None
+    for _ in range(3):
+        nxt = pipe.submit(feats, fg_mask=mask)
+        if pend is not None:
+            pend.result()
+        pend = nxt
+    pend.result()
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 t0 = evs[0].time_range.start
 for e in evs:
-    name = e.name.split("(")[0].split("::")[-1][:48]
+    name = e.name.replace("void ", "").replace("stemseg::(anonymous namespace)::", "").split("(")[0][:60]
     print("%9.1f %8.1f  s%-3s %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
                                      getattr(e, "stream", "?") if hasattr(e, "stream") else "?", name))

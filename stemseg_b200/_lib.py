@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -29,7 +29,7 @@ class StemsegClusterParams(ctypes.Structure):
 
 class StemsegConvShape(ctypes.Structure):
     _fields_ = [("n", c_int32), ("t", c_int32), ("h", c_int32), ("w", c_int32), ("cin", c_int32), ("cout", c_int32),
-                ("kernel_size", c_int32), ("planes", c_int32), ("split_k", c_int32)]
+                ("kernel_size", c_int32), ("planes", c_int32), ("split_k", c_int32), ("tiles_per_cta", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/stemseg_b200.h declares (tests check the two agree)

@@ -43,6 +43,9 @@ struct ConvTcParams {
     int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n * k_slices
     float* out;                // [k_slices][n][t][h][w][cout] fp32 (partial sums when k_slices > 1)
     const float* bias;         // [cout] or nullptr
+    int tiles_per_cta;         // 0: persistent (tile = blockIdx.x + k*gridDim.x); >0: CTA b owns tiles [b*tpc, (b+1)*tpc)
+                               // so that a long layer is a stream of short-lived CTAs and higher-priority kernels of
+                               // other graph branches get SMs while it runs
     int num_stages;            // smem pipeline depth
     float* stat_partial;       // optional [n][cout][tiles_per_sample][2]: per-tile (sum, sum of squares) of every output
                                // channel, consumed by gn_finalize (GroupNorm statistics without re-reading the output)
@@ -250,6 +253,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int k_chunks = p.cin / BLOCK_K;
     const int num_k_blocks = p.taps_per_slice * k_chunks;
+    int tile_first = blockIdx.x, tile_last = p.num_tiles, tile_step = gridDim.x;
+    if (p.tiles_per_cta > 0) {
+        tile_first = blockIdx.x * p.tiles_per_cta;
+        tile_last = tile_first + p.tiles_per_cta < p.num_tiles ? tile_first + p.tiles_per_cta : p.num_tiles;
+        tile_step = 1;
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&a_map0);
@@ -284,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < tile_last; tile += tile_step) {
                 const TileCoord tc = decode_tile(p, tile);
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     const int tap = tc.slice * p.taps_per_slice + kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
@@ -315,7 +324,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_last; tile += tile_step) {
             mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -360,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
         }
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_last; tile += tile_step) {
             const TileCoord tc = decode_tile(p, tile);
             const int t = tc.t0 + dt, h = tc.h0 + dh, w = tc.w0 + dw;
             const bool valid = t < p.t && h < p.h && w < p.w;
@@ -584,6 +593,7 @@ int launch_variant(const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaS
     int grid = device_sm_count();
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > p.num_tiles) grid = p.num_tiles;
+    if (p.tiles_per_cta > 0) grid = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     kernel<<<grid, kNumThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
@@ -689,6 +699,7 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     p.out = out;
     p.bias = bias;
     p.num_stages = 0;
+    p.tiles_per_cta = s->tiles_per_cta > 0 ? s->tiles_per_cta : 0;
     p.tiles_per_sample = p.tiles_t * p.tiles_h * p.tiles_w;
     p.stat_partial = stat_partial;
     SS_REQUIRE(stat_partial == nullptr || (p.k_slices == 1 && head == nullptr),

@@ -107,7 +107,13 @@ def pack_activation(x, planes, out=None):
     return Planes(dst, n, t, h, w, c)
 
 
-def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False):
+# conv launches with at least this many tiles per SM run as short-lived CTAs (CHUNK_TILES consecutive tiles each)
+# instead of one persistent CTA per SM, so that higher-priority branches of the CUDA graph can interleave
+CHUNK_MIN_TILES_PER_SM = 4
+CHUNK_TILES = 2
+
+
+def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked=False):
     """Planes x PackedConv -> fp32 NDHWC tensor [n,t,h,w,cout] (tcgen05 implicit GEMM).
 
     With allow_split the library may split the taps over several CTAs for layers with fewer tiles than SMs; the
@@ -118,7 +124,11 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False):
     if act.planes != packed.planes_tensor.shape[0]:
         raise ValueError("activation / weight precision mismatch")
     shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes,
-                                  1)
+                                  1, 0)
+    if chunked:
+        tiles = lib.stemseg_conv3d_tiles_per_sample(shape) * act.n * max(1, packed.cout // 256)
+        if tiles >= CHUNK_MIN_TILES_PER_SM * torch.cuda.get_device_properties(act.tensor.device).multi_processor_count:
+            shape.tiles_per_cta = CHUNK_TILES
     stat = None
     with torch.cuda.device(act.tensor.device):
         if allow_split:
@@ -238,7 +248,7 @@ def fused_merge_head_output(act, packed, y_low, t_scale, spec, max_ctas=0):
     if (act.n, act.t, act.h, act.w) != (n, tl * t_scale, 2 * hl, 2 * wl) or packed.cout != c:
         raise ValueError("fused_merge_head_output: low-res %s does not upsample by (%d,2,2) to %s" % (
             tuple(y_low.shape), t_scale, (act.n, act.t, act.h, act.w, packed.cout)))
-    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, 1, act.planes, 1)
+    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, 1, act.planes, 1, 0)
     with torch.cuda.device(y_low.device):
         p_low = torch.empty((n, tl, hl, wl, spec.n_out), dtype=torch.float32, device=y_low.device)
         _check(lib.stemseg_head_lowres(_lib.ptr(y_low), n * tl * hl * wl, c, _lib.ptr(spec.weight), spec.n_out,
@@ -320,6 +330,7 @@ class HeadSet(object):
         self.use_graph = use_graph
         self.fuse_output_heads = True       # conv_4 merge GEMM + output heads in one kernel (epilogue fusion)
         self.fuse_stats = True              # GroupNorm statistics from the conv epilogue (unsplit layers)
+        self.chunk_long_layers = True       # long layers as short-lived CTAs + high-priority side branches
         self.pools, self.tscale = pool_schedule(num_frames)
         self.first_stage = {}
         for name, _ in BLOCKS:
@@ -329,7 +340,8 @@ class HeadSet(object):
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
     def _branch(self, name, n_stages, a_in, trace):
         """All conv stages of one scale block for every head; returns per-head Planes."""
-        res = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats)
+        res = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats,
+                     chunked=self.chunk_long_layers)
         y, stat = res if self.fuse_stats else (res, None)
         KEEP.extend((y, stat))
         outs, c0 = [], 0
@@ -451,7 +463,7 @@ class HeadSet(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]     # small branches: high priority
         KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]
         with torch.cuda.graph(graph):

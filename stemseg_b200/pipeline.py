@@ -176,7 +176,7 @@ class SubclipPipeline(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]     # small branches: high priority
         from stemseg_b200 import _lib
         D.KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]
