@@ -26,6 +26,7 @@ class PendingStep(object):
         self._counts_host, self._meta_host, self._labels_host = counts_host, meta_host, labels_host
         self._done, self._label_start = done, label_start
         self._result = None
+        self.inputs_consumed = None      # CUDA event: the step no longer reads the caller's feature tensors
 
     def result(self):
         if self._result is not None:
@@ -69,6 +70,7 @@ class SubclipPipeline(object):
             raise ValueError("no seediness source: give a seediness head or an embedding head with seediness_output")
         self.fuse_heads = True          # run all heads as one HeadSet (shared im2col operand, one CUDA graph)
         self.use_step_graph = True      # heads + compaction + gather + clustering replayed as one CUDA graph
+        self.steps_in_flight = 2        # independent graph instances used round-robin by submit()
         self._group = None
         self._group_key = None
 
@@ -199,19 +201,32 @@ class SubclipPipeline(object):
         if emb_in[0].shape[0] != 1:
             raise ValueError("SubclipPipeline processes one sub-clip at a time (batch dimension must be 1)")
         dev = emb_in[0].device
-        key = (tuple(tuple(f.shape) for f in emb_in), str(dev),
-               None if fg_mask is None else (tuple(fg_mask.shape), fg_mask.dtype),
-               tuple(id(sp) for sp in self._head_group().specs))
         if not hasattr(self, "_step_graphs"):
             self._step_graphs = {}
+            self._instance = 0
+        # `steps_in_flight` independent instances (own static buffers, own stream) are used round-robin, so the
+        # latency-bound tail of step i (merges, clustering) overlaps the convolutions of step i+1
+        self._instance = (self._instance + 1) % max(1, self.steps_in_flight)
+        key = (tuple(tuple(f.shape) for f in emb_in), str(dev),
+               None if fg_mask is None else (tuple(fg_mask.shape), fg_mask.dtype),
+               tuple(id(sp) for sp in self._head_group().specs), self._instance)
         with torch.cuda.device(dev):
             entry = self._step_graphs.get(key)
             if entry is None:
                 entry = self._step_graphs[key] = self._capture_step(emb_in, fg_mask)
+                entry["stream"] = torch.cuda.Stream(device=dev)
+            caller = torch.cuda.current_stream(dev)
+            run_stream = entry["stream"] if self.steps_in_flight > 1 else caller
+            if run_stream is not caller:
+                run_stream.wait_stream(caller)                  # the caller's features / mask are ready
+            stream_ctx = torch.cuda.stream(run_stream)
+            stream_ctx.__enter__()
             for f, pl in zip(emb_in, entry["in_planes"]):
                 D.pack_activation(f, entry["planes"], out=pl)
             if fg_mask is not None:
                 entry["mask"].copy_(fg_mask)
+            consumed = torch.cuda.Event()
+            consumed.record(run_stream)                         # inputs may be overwritten after this point
             entry["graph"].replay()
             _lib.KERNEL_LAUNCHES[0] += entry["kernels"]
             st = entry["state"]
@@ -228,8 +243,15 @@ class SubclipPipeline(object):
                 labels_host = torch.empty(snap["labels"].shape, dtype=torch.int64, pin_memory=True)
                 labels_host.copy_(snap["labels"], non_blocking=True)
             done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream(dev))
-        return PendingStep(self, st, snap, counts_host, meta_host, labels_host, done, int(cluster_label_start))
+            done.record(run_stream)
+            stream_ctx.__exit__(None, None, None)
+            for f in emb_in:                      # keep the caller's tensors alive for the side stream (allocator)
+                f.record_stream(run_stream)
+            if fg_mask is not None:
+                fg_mask.record_stream(run_stream)
+        pend = PendingStep(self, st, snap, counts_host, meta_host, labels_host, done, int(cluster_label_start))
+        pend.inputs_consumed = consumed
+        return pend
 
     @torch.no_grad()
     def run_graphed(self, features, fg_mask=None, cluster_label_start=1):
@@ -267,7 +289,7 @@ class HostFeatureStream(object):
     current (compute) stream wait for them; ``release`` tells the stager the compute stream is done reading the
     buffer.  The H2D transfer of clip i+1 (282 MB at 480p) thereby overlaps the kernels of clip i."""
 
-    def __init__(self, device, depth=2):
+    def __init__(self, device, depth=3):
         self.device = torch.device(device)
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -296,10 +318,12 @@ class HostFeatureStream(object):
         torch.cuda.current_stream(self.device).wait_event(self._ready[ticket])
         return self._buffers[ticket]
 
-    def release(self, ticket):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
-        self._free[ticket] = ev
+    def release(self, ticket, event=None):
+        """The buffer may be refilled once `event` (default: everything enqueued so far on the current stream) is done."""
+        if event is None:
+            event = torch.cuda.Event()
+            event.record(torch.cuda.current_stream(self.device))
+        self._free[ticket] = event
 
 
 def build_davis_pipeline(device, num_frames=8, precision="fp32", in_channels=256,
