@@ -383,9 +383,18 @@ def run_gpu_arm(args, rank, local_rank, world):
     conv_ms_per_step = sum(sum(v) for v in by_shape.values()) / args.steps
     dom_count_per_step = len(dom_times) / args.steps
     planes_products = 3 if planes == 2 else 1
+    traffic, traffic_src = None, None
+    try:            # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_full_summary.json")))
+        dom = prof["dominant_conv"]
+        if args.precision == "fp32" and "256, 32, 2" in dom["Kernel Name"]:
+            traffic = (float(dom["dram__bytes_read.sum"]) + float(dom["dram__bytes_write.sum"])) * 1e6
+            traffic_src = "profiles/r01_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, bytes/launch)"
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+        "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
         "kernel": "conv_tc_kernel %dx%dx%dx%d cin=%d cout=%d k=%d planes=%d" % (n * t, h, w, 1, cin, cout, ks, planes),
         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
         "algorithmic_gflop_per_launch": flops / 1e9,
