@@ -457,6 +457,140 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[2] and configs[3]); the default line is configs[1]
+# ------------------------------------------------------------------------------------------------------------------
+def run_cfg3(args, rank, local_rank, world):
+    """configs[2]: 16x480x864 clip, bf16 decoder (tcgen05, one product per MAC) + clustering; plus the clustering
+    kernel alone on 8-dim embeddings with 8 learned variances (N = 414 720 quarter-res, 6 635 520 full-res)."""
+    import numpy as np
+    import torch
+    from stemseg_b200 import _lib
+    from stemseg_b200.clusterers import SequentialClustering
+    from stemseg_b200.pipeline import build_davis_pipeline
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().stemseg_check_device())
+    t16 = 16
+    pipe = build_davis_pipeline(device, num_frames=t16, precision="bf16")
+    g = torch.Generator().manual_seed(0)
+    feats = {s_: torch.randn(1, IN_CH, t16, HP // s_, WP // s_, generator=g).to(device) for s_ in (32, 16, 8, 4)}
+    mask = torch.ones((t16, H4, W4), dtype=torch.uint8, device=device)
+    for _ in range(max(3, args.warmup)):
+        pipe(feats, fg_mask=mask)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    queue = []
+    for _ in range(args.steps):
+        queue.append(pipe.submit(feats, fg_mask=mask))
+        if len(queue) > pipe.steps_in_flight:
+            queue.pop(0).result()
+    for q in queue:
+        q.result()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    flops = 2 * 2 * 564.87e9                     # two heads, SURVEY §8d: 564.87 GMAC per head at 16x480x864
+    extra = {}
+    rng = np.random.default_rng(0)
+    for n in (t16 * H4 * W4, t16 * HP * WP):
+        centres = rng.uniform(-1, 1, size=(24, 8)).astype(np.float32)
+        which = rng.integers(0, 24, size=n)
+        emb = torch.from_numpy(centres[which] + 0.05 * rng.standard_normal((n, 8)).astype(np.float32)).to(device)
+        bw = torch.from_numpy(np.exp(rng.uniform(-1, 1, size=(n, 8))).astype(np.float32) * 10).to(device)
+        seed = torch.rand(n, device=device)
+        clu = SequentialClustering(0.5, 0.3, 0.0, 0, [], device)
+        pend = clu.launch(emb, bw, seed, 1)
+        _, meta = clu.finish(pend)
+        k = len(meta["instance_labels"])
+        times = []
+        for _ in range(5):
+            a.record()
+            clu.launch(emb, bw, seed, 1)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        t_ms = sorted(times)[2]
+        byts = n * (4 * 8 + 12) * (k + 1)
+        extra["cluster_e8_n%d" % n] = {"ms": t_ms, "clusters": k, "algorithmic_gb_per_s": byts / t_ms / 1e6,
+                                       "frac_of_hbm_peak": byts / t_ms / 1e6 / load_peaks()["hbm_gbs"]}
+    print(json.dumps({"metric": "clips_per_sec", "value": 1e3 / ms, "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "configs[2]: 16x480x854 clip (pad 480x864), DAVIS heads in bf16 + fg gather + "
+                                             "clustering over 414720 points; clustering alone on E=8"},
+                      "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                      "frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / load_peaks()["bf16_tflops_sustained"],
+                      **extra}), flush=True)
+
+
+def run_video64(args, rank, local_rank, world):
+    """configs[3]: a 64-frame sequence = 8 overlapping 16-frame sub-clips (get_subsequence_frames(64, 16, overlap 9)),
+    clip-parallel: sub-clip i on rank i % world, NCCL all-gather of the label vectors, sequential stitch on every rank."""
+    import torch
+    import torch.distributed as dist
+    from stemseg_b200 import _lib
+    from stemseg_b200.chaining import get_subsequence_frames
+    from stemseg_b200.parallel import clip_parallel_process
+    from stemseg_b200.pipeline import build_davis_pipeline
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().stemseg_check_device())
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    t16 = 16
+    windows, _ = get_subsequence_frames(64, t16, "davis", 9)
+    pipe = build_davis_pipeline(device, num_frames=t16, min_seediness_prob=0.0)
+    cache = {}
+
+    def features_for_clip(i):
+        if i not in cache:
+            g = torch.Generator().manual_seed(1000 + i)
+            cache[i] = {s_: torch.randn(1, IN_CH, t16, HP // s_, WP // s_, generator=g).to(device) for s_ in (32, 16, 8, 4)}
+        return cache[i]
+
+    for i in range(len(windows)):
+        if i % world == rank:
+            features_for_clip(i)
+    masks = torch.ones((64, H4, W4), dtype=torch.uint8, device=device)
+
+    def one_video():
+        container, _, _ = clip_parallel_process(pipe, masks, windows, features_for_clip)
+        return container
+
+    for _ in range(2):
+        one_video()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = max(2, args.steps // 5)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        container = one_video()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / reps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        labels, counts, lifetimes = container.get_track_mask_idxes()
+        print(json.dumps({"metric": "subclips_per_sec", "value": len(windows) / dt, "unit": "sub-clips/s",
+                          "n_gpus": world, "steps": reps, "warmup": 2, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "configs[3]: 64-frame video, 8 sub-clips of 16x480x864 (overlap 9), "
+                                                 "clip-parallel heads+gather+clustering, all-gather of labels, stitch",
+                                     "timing": "host wall clock around the whole video (includes the exchange and the "
+                                               "host-side stitch), max over ranks"},
+                          "videos_per_sec": 1.0 / dt, "tracks": len([k for k in counts if k >= 0])}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,6 +599,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="davis480p", choices=["davis480p", "cfg3", "video64"],
+                    help="davis480p = BASELINE configs[1] (the contract line); cfg3 / video64 = configs[2] / configs[3]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -478,6 +614,10 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
                              "--master-addr 127.0.0.1 --master-port 29500 bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    if args.workload == "cfg3":
+        return run_cfg3(args, rank, local_rank, world)
+    if args.workload == "video64":
+        return run_video64(args, rank, local_rank, world)
     run_gpu_arm(args, rank, local_rank, world)
 
 

@@ -296,3 +296,33 @@ def test_submit_result_pipelining(cuda_device):
         assert torch.equal(a.embeddings, b.embeddings)
         assert torch.equal(b.labels_host, b.labels.cpu())
         assert a.fg_index.frame_counts == b.fg_index.frame_counts
+
+
+def test_head_without_normalisation(cuda_device):
+    """NORMALIZATION_LAYER 'none' (model_builder.py:33): NormType=nn.Identity -> conv, ReLU, pool only."""
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    shapes = do.head_parameter_shapes("seediness", 32, [32, 32, 32, 32], gn=False)
+    sd = do.seeded_state_dict(shapes, 77)
+    feats = do.seeded_features(78, 1, 32, 8, 24, 24)
+    head = heads.SeedinessHead(32, [32, 32, 32, 32], PoolType=nn.AvgPool3d, NormType=nn.Identity, num_frames=8)
+    head.load_state_dict(sd, strict=True)
+    head = head.to(cuda_device).eval()
+    with torch.no_grad():
+        out = head([f.to(cuda_device) for f in feats])
+    ref = do.seediness_head(sd, feats, 8, gn_groups=0)
+    err = (out.cpu().double() - ref.double()).abs().max().item() / ref.abs().max().item()
+    assert err <= FP32_TOL, err
+
+
+def test_unsupported_options_fail_loudly():
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    with pytest.raises(NotImplementedError):
+        heads.SeedinessHead(32, [32] * 4, PoolType=nn.MaxPool3d, num_frames=8)
+    with pytest.raises(NotImplementedError):
+        heads.SeedinessHead(32, [32] * 4, NormType=nn.BatchNorm3d, num_frames=8)
+    with pytest.raises(NotImplementedError):
+        heads.SeedinessHead(32, [32] * 4, num_frames=7)
+    with pytest.raises(ValueError):
+        heads.SeedinessHead(48, [32] * 4, num_frames=8)
