@@ -103,24 +103,25 @@ def associate_label_sets(labels_1, labels_2):
     a = labels_1.cpu().numpy() if torch.is_tensor(labels_1) else np.asarray(labels_1)
     b = labels_2.cpu().numpy() if torch.is_tensor(labels_2) else np.asarray(labels_2)
     assert a.shape == b.shape, "Shape mismatch: {}, {}".format(a.shape, b.shape)
+    # one joint histogram over the raw label values gives every count that is needed (labels are small ints >= -1)
+    a1 = a.astype(np.int64) + 1
+    b1 = b.astype(np.int64) + 1
+    assert a1.size == 0 or (a1.min() >= 0 and b1.min() >= 0), "labels below the outlier label -1"
+    na = int(a1.max()) + 1 if a1.size else 1
+    nb = int(b1.max()) + 1 if b1.size else 1
+    joint = np.bincount(a1 * nb + b1, minlength=na * nb).reshape(na, nb)
+    size_a, size_b = joint.sum(1), joint.sum(0)
     # the reference builds the label lists through python sets (online_chainer.py:307-308); keep its ordering
-    unique_1 = list(set(np.unique(a).tolist()) - {OUTLIER_LABEL})
-    unique_2 = list(set(np.unique(b).tolist()) - {OUTLIER_LABEL})
+    unique_1 = list(set((np.nonzero(size_a)[0] - 1).tolist()) - {OUTLIER_LABEL})
+    unique_2 = list(set((np.nonzero(size_b)[0] - 1).tolist()) - {OUTLIER_LABEL})
     assert not set(unique_1).intersection(set(unique_2)), "Labels overlap: {}, {}".format(unique_1, unique_2)
     costs = np.zeros((len(unique_1), len(unique_2)), np.float32)
     recall = np.zeros((len(unique_1), len(unique_2)), np.float32)
     if unique_1 and unique_2:
-        pos1 = {l: i for i, l in enumerate(unique_1)}
-        pos2 = {l: i for i, l in enumerate(unique_2)}
-        i1 = np.array([pos1.get(v, -1) for v in a.tolist()], np.int64) if a.size < 64 else \
-            np.vectorize(lambda v: pos1.get(v, -1), otypes=[np.int64])(a)
-        i2 = np.array([pos2.get(v, -1) for v in b.tolist()], np.int64) if b.size < 64 else \
-            np.vectorize(lambda v: pos2.get(v, -1), otypes=[np.int64])(b)
-        n1, n2 = len(unique_1), len(unique_2)
-        both = (i1 >= 0) & (i2 >= 0)
-        inter = np.bincount(i1[both] * n2 + i2[both], minlength=n1 * n2).reshape(n1, n2)     # joint histogram
-        size1 = np.bincount(i1[i1 >= 0], minlength=n1)
-        size2 = np.bincount(i2[i2 >= 0], minlength=n2)
+        r = np.array(unique_1, np.int64) + 1
+        c = np.array(unique_2, np.int64) + 1
+        inter = joint[np.ix_(r, c)]
+        size1, size2 = size_a[r], size_b[c]
         union = size1[:, None] + size2[None, :] - inter
         iou = inter.astype(np.float32) / union.astype(np.float32)          # fp32 division like the torch ops
         costs = (1.0 - iou.astype(np.float64)).astype(np.float32)          # 1. - iou.item() stored as fp32

@@ -86,9 +86,26 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     local = {}
+
+    def collect(i, pend):
+        res = pend.result()
+        counts = res.fg_index.frame_counts
+        host = res.labels_host if res.labels_host is not None else res.labels.cpu()
+        local[i] = (list(host.split(counts, 0)), res.meta)
+
+    queue = []
+    depth = max(1, getattr(pipeline, "steps_in_flight", 1))
     for i in shard_subclips(len(subseq_frames), rank, world):
         fg_mask = None if masks is None else masks[subseq_frames[i]]
-        res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
-        local[i] = ([l.cpu() for l in res.frame_labels], res.meta)
+        if hasattr(pipeline, "submit") and getattr(pipeline, "use_step_graph", False):
+            queue.append((i, pipeline.submit(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1,
+                                             labels_to_host=True)))
+            if len(queue) > depth:
+                collect(*queue.pop(0))
+        else:
+            res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
+            local[i] = ([l.cpu() for l in res.frame_labels], res.meta)
+    for item in queue:
+        collect(*item)
     num_frames = max(max(f) for f in subseq_frames) + 1
     return exchange_and_stitch(num_frames, subseq_frames, local, group=group)
