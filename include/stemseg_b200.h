@@ -228,6 +228,20 @@ int32_t stemseg_conv1x1_head_output(const void* act_planes, const void* weight_p
                                     const float* out_bias, const int32_t* activation, const int32_t* coordinate,
                                     int32_t n_out, float time_scale, float* out, int32_t max_ctas, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Sub-clip stitch on the device
+ *   replaces the K1*K2 mask reductions of OnlineChainer.associate_clusters      online_chainer.py:315-328
+ *            the per-association torch.where relabelling                        online_chainer.py:219-224
+ *            the per-frame unique / count loops of get_track_mask_idxes         online_chainer.py:94-117
+ * table[ia][ib] counts the points with bin(a) == ia and bin(b) == ib, where bin(v) = 0 for v < 0 (outliers) and
+ * v - base + 1 otherwise; values outside the table increment *out_of_range (caller error).  Intersection, sizes and
+ * unions of every label pair follow from this one table; the Hungarian solve stays on the host.
+ * ---------------------------------------------------------------------------------------------------------- */
+int32_t stemseg_label_pair_histogram(const int64_t* a, const int64_t* b, int64_t n, int64_t a_base, int64_t b_base,
+                                     int32_t na, int32_t nb, int32_t* table, int32_t* out_of_range, void* stream);
+/* labels[i] = lut[labels[i] - base] for labels[i] >= base (negative labels and labels outside the table unchanged) */
+int32_t stemseg_relabel_lut(int64_t* labels, int64_t n, int64_t base, const int64_t* lut, int32_t nlut, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

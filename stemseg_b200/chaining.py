@@ -163,12 +163,19 @@ def stitch_subsequences(num_frames, subseq_frames, subseq_local_labels, subseq_m
         existing = container.get_labels(overlapping)
         current = [labels[j] for j, t in enumerate(frames) if t in overlapping]
         associations, _, _, _, _ = associate_label_sets(torch.cat(existing), torch.cat(current))
+        # relabel the non-overlap frames: the reference applies the (associated <- current) substitutions one after
+        # the other (online_chainer.py:219-224); current labels are >= next_track_label and associated ones are
+        # smaller, so the substitutions never chain and one lookup table is equivalent
+        top = max([int(l.max()) for l in labels if l.numel() > 0] + [0])
+        lut = torch.arange(-1, top + 1, dtype=torch.int64)            # index = label + 1
+        for associated_label, current_label in associations:
+            if current_label <= top:
+                lut[current_label + 1] = associated_label
+        overlap_set = set(overlapping)
         for j, t in enumerate(frames):
-            if t in overlapping:
+            if t in overlap_set:
                 continue
-            for associated_label, current_label in associations:
-                labels[j] = torch.where(labels[j] == current_label, torch.tensor(associated_label).to(labels[j]),
-                                        labels[j])
+            labels[j] = lut[labels[j] + 1]
             next_track_label = container.add_labels([t], [labels[j]])
         if meta is not None:
             for associated_label, current_label in associations:
@@ -229,3 +236,149 @@ class OnlineChainer(object):
                 fg_embeddings.append(fg_emb.cpu())
         container, subseq_labels_list, meta_out = stitch_subsequences(num_frames, frames_list, local_labels, metas)
         return container.get_track_mask_idxes(), mask_idxes, subseq_labels_list, fg_embeddings, meta_out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-side stitch: labels never leave the GPU; per sub-clip two histogram launches, one
+# <= 21 x 21 table on the host for the Hungarian solve, one LUT relabel launch
+# ----------------------------------------------------------------------------------------------------------------
+class DeviceTrackContainer(object):
+    """Result of ``stitch_subsequences_device``: per-frame label tensors on the device + host-side statistics."""
+
+    def __init__(self, frame_labels, counts, spans):
+        self._frame_labels, self._counts, self._spans = frame_labels, counts, spans
+
+    def get_labels(self, frame_nums):
+        return [self._frame_labels[t] for t in frame_nums]
+
+    def get_track_mask_idxes(self):
+        lifetimes = {k: v[1] - v[0] for k, v in self._spans.items()}
+        return self._frame_labels, self._counts, lifetimes
+
+
+def _pair_histogram(a, b, a_base, b_base, na, nb):
+    from stemseg_b200 import _lib
+    lib = _lib.load()
+    dev = a.device
+    with torch.cuda.device(dev):
+        table = torch.empty((na, nb), dtype=torch.int32, device=dev)
+        bad = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.stemseg_label_pair_histogram(_lib.ptr(a), _lib.ptr(b), a.numel(), a_base, b_base, na, nb,
+                                                    _lib.ptr(table), _lib.ptr(bad), _lib.stream_ptr()))
+    return table, bad
+
+
+def _relabel(labels, base, lut_host):
+    from stemseg_b200 import _lib
+    lib = _lib.load()
+    if labels.numel() == 0:
+        return
+    with torch.cuda.device(labels.device):
+        lut = torch.tensor(lut_host, dtype=torch.int64, device=labels.device)
+        _lib.check(lib.stemseg_relabel_lut(_lib.ptr(labels), labels.numel(), base, _lib.ptr(lut), len(lut_host),
+                                           _lib.stream_ptr()))
+
+
+@torch.no_grad()
+def stitch_subsequences_device(num_frames, subseq_frames, subseq_labels, subseq_counts, subseq_num_clusters,
+                               subseq_meta=None):
+    """Same result as ``stitch_subsequences`` with the label vectors resident on the device.
+
+    subseq_labels[i]: contiguous int64 CUDA tensor with the LOCAL labels (cluster_label_start=1) of all frames of
+    sub-clip i; subseq_counts[i]: per-frame point counts (python ints); subseq_num_clusters[i]: K_i.
+    Returns (DeviceTrackContainer, per-sub-clip relabelled tensors, metas)."""
+    frame_labels = [None] * num_frames
+    counts = defaultdict(lambda: 0)
+    spans = defaultdict(lambda: [10000, -1])
+    highest = 0
+    next_track_label = 1
+    out_labels, out_meta = [], []
+
+    def account(frames_added, table, lut_local):
+        """table[local bin][frame slot + 1] -> global counts / lifetimes / highest id for the frames just added."""
+        nonlocal highest
+        for slot, t in frames_added:
+            col = table[:, slot + 1]
+            for bin_, c in enumerate(col.tolist()):
+                if c == 0:
+                    continue
+                label = -1 if bin_ == 0 else lut_local[bin_ - 1]
+                counts[label] += c
+                spans[label][0] = min(t, spans[label][0])
+                spans[label][1] = max(t, spans[label][1])
+                if label > highest:
+                    highest = label
+
+    for i, frames in enumerate(subseq_frames):
+        labels = subseq_labels[i].clone()
+        cnts = list(subseq_counts[i])
+        k = int(subseq_num_clusters[i])
+        dev = labels.device
+        offset = next_track_label - 1
+        starts = [0]
+        for c in cnts:
+            starts.append(starts[-1] + c)
+        frame_ids = torch.repeat_interleave(torch.arange(len(frames), device=dev),
+                                            torch.tensor(cnts, device=dev)).to(torch.int64)
+        per_frame, bad0 = _pair_histogram(labels, frame_ids, 1, 0, k + 2, len(frames) + 1)      # [local bin][slot+1]
+        meta = None
+        if subseq_meta is not None:
+            meta = dict(subseq_meta[i])
+            meta['instance_labels'] = [l + offset for l in meta['instance_labels']]
+        lut_local = [l + offset for l in range(1, k + 2)]           # local label l -> global label (index l - 1)
+        if i == 0:
+            per_frame_h = per_frame.cpu().numpy()
+            _relabel(labels, 1, lut_local)
+            for j, t in enumerate(frames):
+                frame_labels[t] = labels[starts[j]:starts[j + 1]]
+            account(list(enumerate(frames)), per_frame_h, lut_local)
+        else:
+            prev = subseq_frames[i - 1]
+            overlap_set = set(frames).intersection(set(prev))
+            overlapping = sorted(list(overlap_set))
+            existing = torch.cat([frame_labels[t] for t in overlapping])
+            current = torch.cat([labels[starts[j]:starts[j + 1]] for j, t in enumerate(frames) if t in overlap_set])
+            na = next_track_label + 1
+            joint, bad1 = _pair_histogram(existing, current, 1, 1, na, k + 2)
+            joint_h = joint.cpu().numpy().astype(np.int64)           # sync: the small tables
+            per_frame_h = per_frame.cpu().numpy()
+            assert int(bad0.item()) == 0 and int(bad1.item()) == 0, "label outside the histogram range"
+            size_a, size_b = joint_h.sum(1), joint_h.sum(0)
+            # the reference builds these lists through python sets (online_chainer.py:307-308); keep its ordering
+            unique_1 = list(set(np.nonzero(size_a[1:])[0] + 1))
+            unique_1 = [int(v) for v in unique_1]
+            unique_2 = list(set(int(v) + 1 + offset for v in np.nonzero(size_b[1:])[0]))
+            assert not set(unique_1).intersection(set(unique_2)), "Labels overlap: {}, {}".format(unique_1, unique_2)
+            costs = np.zeros((len(unique_1), len(unique_2)), np.float32)
+            if unique_1 and unique_2:
+                r = np.array(unique_1, np.int64)
+                c = np.array(unique_2, np.int64) - offset
+                inter = joint_h[np.ix_(r, c)]
+                union = size_a[r][:, None] + size_b[c][None, :] - inter
+                iou = inter.astype(np.float32) / union.astype(np.float32)
+                costs = (1.0 - iou.astype(np.float64)).astype(np.float32)
+            rows, cols = linear_sum_assignment(costs)
+            associations = [(unique_1[r_], unique_2[c_]) for r_, c_ in zip(rows, cols)]
+            lut_assoc = list(lut_local)
+            for associated_label, current_label in associations:
+                lut_assoc[current_label - offset - 1] = associated_label
+            # overlap frames keep the raw (offset) labels in the returned sub-clip labels and are NOT added to the
+            # container; non-overlap frames are relabelled through the association table
+            added = []
+            for j, t in enumerate(frames):
+                seg = labels[starts[j]:starts[j + 1]]
+                if t in overlap_set:
+                    _relabel(seg, 1, lut_local)
+                else:
+                    _relabel(seg, 1, lut_assoc)
+                    frame_labels[t] = seg
+                    added.append((j, t))
+            account(added, per_frame_h, lut_assoc)
+            if meta is not None:
+                for associated_label, current_label in associations:
+                    idx = meta['instance_labels'].index(current_label)
+                    meta['instance_labels'][idx] = associated_label
+        next_track_label = highest + 1
+        out_labels.append(labels)
+        out_meta.append(meta)
+    return DeviceTrackContainer(frame_labels, counts, spans), out_labels, out_meta
