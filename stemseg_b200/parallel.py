@@ -11,7 +11,7 @@ right tool (no custom transport).
 import torch
 import torch.distributed as dist
 
-from stemseg_b200.chaining import stitch_subsequences
+from stemseg_b200.chaining import stitch_subsequences, stitch_subsequences_device
 
 
 def shard_subclips(num_subclips, rank, world_size):
@@ -77,6 +77,54 @@ def exchange_and_stitch(num_frames, subseq_frames, local_results, group=None, de
                                [meta_by_clip[i] for i in range(n_sub)])
 
 
+def exchange_and_stitch_device(num_frames, subseq_frames, local_results, group=None):
+    """Device-resident variant: local_results = {i: (int64 CUDA tensor of all local labels of sub-clip i, per-frame
+    counts, meta)}.  One NCCL all_gather of the (padded) label vectors + one of the counts; the stitch then runs on the
+    device of every rank (stemseg_b200.chaining.stitch_subsequences_device)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_sub = len(subseq_frames)
+    if world > 1:
+        owned = shard_subclips(n_sub, rank, world)
+        assert sorted(local_results.keys()) == owned
+        device = next(iter(local_results.values()))[0].device if local_results else torch.device(
+            "cuda", torch.cuda.current_device())
+        max_local = (n_sub + world - 1) // world
+        max_t = max(len(f) for f in subseq_frames)
+        counts = torch.full((max_local, max_t), -1, dtype=torch.int64)
+        for slot, i in enumerate(owned):
+            counts[slot, :len(local_results[i][1])] = torch.tensor(local_results[i][1], dtype=torch.int64)
+        counts = counts.to(device)
+        all_counts = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(all_counts, counts, group=group)
+        all_counts = torch.stack(all_counts).cpu()
+        totals = all_counts.clamp(min=0).sum(dim=(1, 2)).tolist()
+        pad_to = max(max(totals), 1)
+        buf = torch.full((pad_to,), -2, dtype=torch.int64, device=device)
+        mine = [local_results[i][0] for i in owned]
+        if mine:
+            flat = torch.cat(mine)
+            buf[:flat.numel()] = flat
+        all_labels = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(all_labels, buf, group=group)
+        all_metas = [None] * world
+        dist.all_gather_object(all_metas, {i: local_results[i][2] for i in owned}, group=group)
+        gathered = {}
+        for r in range(world):
+            cursor = 0
+            for slot, i in enumerate(shard_subclips(n_sub, r, world)):
+                cnt = [int(c) for c in all_counts[r, slot, :len(subseq_frames[i])]]
+                n_i = sum(cnt)
+                gathered[i] = (all_labels[r][cursor:cursor + n_i], cnt, all_metas[r][i])
+                cursor += n_i
+        local_results = gathered
+    labels = [local_results[i][0] for i in range(n_sub)]
+    counts = [local_results[i][1] for i in range(n_sub)]
+    metas = [local_results[i][2] for i in range(n_sub)]
+    ks = [len(m["instance_labels"]) for m in metas]
+    return stitch_subsequences_device(num_frames, subseq_frames, labels, counts, ks, metas)
+
+
 @torch.no_grad()
 def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, group=None):
     """Run the owned sub-clips through ``pipeline`` (stemseg_b200.pipeline.SubclipPipeline) and stitch globally.
@@ -89,23 +137,20 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
 
     def collect(i, pend):
         res = pend.result()
-        counts = res.fg_index.frame_counts
-        host = res.labels_host if res.labels_host is not None else res.labels.cpu()
-        local[i] = (list(host.split(counts, 0)), res.meta)
+        local[i] = (res.labels, list(res.fg_index.frame_counts), res.meta)
 
     queue = []
     depth = max(1, getattr(pipeline, "steps_in_flight", 1))
     for i in shard_subclips(len(subseq_frames), rank, world):
         fg_mask = None if masks is None else masks[subseq_frames[i]]
         if hasattr(pipeline, "submit") and getattr(pipeline, "use_step_graph", False):
-            queue.append((i, pipeline.submit(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1,
-                                             labels_to_host=True)))
+            queue.append((i, pipeline.submit(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)))
             if len(queue) > depth:
                 collect(*queue.pop(0))
         else:
             res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
-            local[i] = ([l.cpu() for l in res.frame_labels], res.meta)
+            local[i] = (res.labels, list(res.fg_index.frame_counts), res.meta)
     for item in queue:
         collect(*item)
     num_frames = max(max(f) for f in subseq_frames) + 1
-    return exchange_and_stitch(num_frames, subseq_frames, local, group=group)
+    return exchange_and_stitch_device(num_frames, subseq_frames, local, group=group)
