@@ -259,6 +259,67 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
     }
 }
 
+// Pooled variant with column reuse: one thread produces kPoolW consecutive outputs along W for one channel quad; the
+// (t,h)-summed columns are shared between neighbouring outputs (54 loads per 4 outputs instead of 108).
+constexpr int kPoolW = 4;
+
+__global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
+                                                              int n, int t, int h, int w, int c, int t_out, int row_stride,
+                                                              __nv_bfloat16* __restrict__ dst, size_t plane_elems,
+                                                              int planes) {
+    const int quads = c / 4;
+    const int wgroups = (w + kPoolW - 1) / kPoolW;
+    const long long total = 1ll * n * t_out * h * wgroups * quads;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int q = static_cast<int>(i % quads);
+        long long v = i / quads;
+        const int wg = static_cast<int>(v % wgroups); v /= wgroups;
+        const int hh = static_cast<int>(v % h); v /= h;
+        const int to = static_cast<int>(v % t_out);
+        const int nn = static_cast<int>(v / t_out);
+        const int w0 = wg * kPoolW;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (scale_shift) {
+            const float4* tab = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(nn) * c + 4 * q) * 2);
+            const float4 t0 = __ldg(tab), t1 = __ldg(tab + 1);
+            sc[0] = t0.x; sh[0] = t0.y; sc[1] = t0.z; sh[1] = t0.w;
+            sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
+        }
+        float col[kPoolW + 2][4];
+#pragma unroll
+        for (int k = 0; k < kPoolW + 2; ++k) col[k][0] = col[k][1] = col[k][2] = col[k][3] = 0.f;
+        for (int dt = -1; dt <= 1; ++dt) {
+            const int ti = 2 * to + dt;
+            if (ti < 0 || ti >= t) continue;
+            for (int dh = -1; dh <= 1; ++dh) {
+                const int hi = hh + dh;
+                if (hi < 0 || hi >= h) continue;
+                const float* rowp = x + ((static_cast<size_t>(nn) * t + ti) * h + hi) * static_cast<size_t>(w) * row_stride;
+#pragma unroll
+                for (int k = 0; k < kPoolW + 2; ++k) {
+                    const int wi = w0 + k - 1;
+                    if (wi < 0 || wi >= w) continue;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(rowp + static_cast<size_t>(wi) * row_stride) + q);
+                    col[k][0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
+                    col[k][1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+                    col[k][2] += fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
+                    col[k][3] += fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPoolW; ++k) {
+            const int wo = w0 + k;
+            if (wo >= w) break;
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = (col[k][e] + col[k + 1][e] + col[k + 2][e]) * (1.0f / 27.0f);
+            const size_t off = ((((static_cast<size_t>(nn) * t_out + to) * h + hh) * w + wo) * c) + 4 * q;
+            store_planes4(dst, plane_elems, planes, off, r);
+        }
+    }
+}
+
 // flat variant of gn_relu_pool_kernel<false> for row_stride == c and one slice (the big 4x layer): no index
 // decomposition, two independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256) gn_relu_flat_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
@@ -596,7 +657,10 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     const size_t slice_stride = static_cast<size_t>(n) * t * h * w * row_stride;
     const long long total = 1ll * n * t_out * h * w * (c / 4);
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
-    if (pool)
+    if (pool && slices == 1)
+        gn_relu_pool_w4_kernel<<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
+            x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
+    else if (pool)
         gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     else if (slices == 1)
