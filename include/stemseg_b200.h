@@ -242,6 +242,21 @@ int32_t stemseg_label_pair_histogram(const int64_t* a, const int64_t* b, int64_t
 /* labels[i] = lut[labels[i] - base] for labels[i] >= base (negative labels and labels outside the table unchanged) */
 int32_t stemseg_relabel_lut(int64_t* labels, int64_t n, int64_t base, const int64_t* lut, int32_t nlut, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Instance-mask writeback
+ *   replaces label scatter -> one-hot -> x4 bilinear -> crop -> bilinear resize -> "> 0.5" -> condensation
+ *            stemseg/inference/output_utils/davis.py:76-112 (youtube_vis.py:117-161, kitti_mots.py:101-166)
+ * stemseg_rank_map_scatter: rank_map[indices[i]] = lut[labels[i]] into a zeroed uint8 map of map_elems voxels
+ *   (lut: track id -> rank + 1 among the instances to keep, 0 = dropped; ids outside the table / negative -> 0).
+ * stemseg_mask_writeback: out[f][y][x] = rank of the unique instance whose two-stage interpolated one-hot mask exceeds
+ *   0.5 at that pixel (0 if none): rank_map [frames][h][w] is up-sampled by `upscale` (bilinear, align_corners=False),
+ *   cropped to crop_h x crop_w and resized to out_h x out_w (bilinear), in the reference's fp32 evaluation order.
+ * ---------------------------------------------------------------------------------------------------------- */
+int32_t stemseg_rank_map_scatter(const int32_t* indices, const int64_t* labels, int64_t n, const uint8_t* lut,
+                                 int32_t nlut, uint8_t* rank_map, int64_t map_elems, void* stream);
+int32_t stemseg_mask_writeback(const uint8_t* rank_map, int32_t frames, int32_t h, int32_t w, int32_t upscale,
+                               int32_t crop_h, int32_t crop_w, int32_t out_h, int32_t out_w, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

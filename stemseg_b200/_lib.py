@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -52,6 +52,9 @@ PROTOTYPES = {
     "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                                c_void_p, c_void_p, c_void_p]),
     "stemseg_relabel_lut": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "stemseg_rank_map_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "stemseg_mask_writeback": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                         c_int32, c_void_p, c_void_p]),
     "stemseg_pack_activation": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_int32, c_void_p]),
     "stemseg_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
@@ -91,10 +94,14 @@ KERNELS_PER_CALL = {
     "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                                c_void_p, c_void_p, c_void_p]),
     "stemseg_relabel_lut": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "stemseg_rank_map_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "stemseg_mask_writeback": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                         c_int32, c_void_p, c_void_p]),
     "stemseg_pack_activation": 1, "stemseg_pack_conv_weight": 1, "stemseg_conv3d_bf16_planes": 1,
     "stemseg_group_norm_stats": 2, "stemseg_group_norm_finalize": 1, "stemseg_norm_relu_pool": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
     "stemseg_head_lowres": 1, "stemseg_conv1x1_head_output": 1,
     "stemseg_label_pair_histogram": 1, "stemseg_relabel_lut": 1,
+    "stemseg_rank_map_scatter": 1, "stemseg_mask_writeback": 1,
 }
 
 
