@@ -120,6 +120,22 @@ int32_t stemseg_fg_compact(const uint8_t* mask, int64_t n_frames, int64_t frame_
 int32_t stemseg_fg_compact_threshold(const float* values, float threshold, int64_t n_frames, int64_t frame_voxels,
                                      int32_t* indices, int32_t* frame_counts, void* workspace,
                                      size_t workspace_bytes, void* stream);
+/* Foreground from per-frame running sums: fg = upsample(sum / count[frame], (1, factor, factor)) > threshold on the
+ * [T][factor*h][factor*w] grid -- the seediness / foreground-logit average over the sub-clips covering a frame
+ * (stemseg/inference/main.py:93-103; inference_model.py:126-128,207), at full resolution when factor = 4
+ * (--resize_embeddings: inference_model.py:55-61, online_chainer.py:128-140). */
+int32_t stemseg_fg_compact_mean_threshold(const float* sum, const float* count, float threshold, int64_t n_frames,
+                                          int32_t h, int32_t w, int32_t factor, int32_t* indices,
+                                          int32_t* frame_counts, void* workspace, size_t workspace_bytes, void* stream);
+/* dst[frame_ids[j]] += src[j] for the `frames` planes of one sub-clip; counts[frame_ids[j]] += 1 */
+int32_t stemseg_frame_accumulate(float* dst, float* counts, const float* src, const int32_t* frame_ids, int32_t frames,
+                                 int64_t plane, void* stream);
+/* stemseg_fg_gather with the trilinear (1, factor, factor) up-sampling of online_chainer.py:128-140 fused in:
+ * `indices` address the full-resolution grid [T][factor*h][factor*w], src is the [C][T][h][w] map; transform 1
+ * activates (exp * 10) the corner values before interpolating, like the reference resizes activated bandwidths. */
+int32_t stemseg_fg_gather_upsampled(const float* src, int64_t channel_stride, int32_t channels, int32_t h, int32_t w,
+                                    int32_t factor, const int32_t* indices, int64_t n, const int32_t* n_dev,
+                                    int32_t transform, float* dst, void* stream);
 /*
  * src       device float [C][T*HW] channel-first map, channel stride `channel_stride` elements
  * indices   device int32 [n]

@@ -26,3 +26,33 @@ def gather_map(coords, channel_first):
 
 def gather_foreground(coords, embeddings, bandwidths, seediness):
     return gather_map(coords, embeddings), gather_map(coords, bandwidths), gather_map(coords, seediness)
+
+
+def resize_map(channel_first, factor):
+    """online_chainer.py:128-140 / inference_model.py:55-61: trilinear (1, s, s), align_corners=False (torch CPU)."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.from_numpy(np.ascontiguousarray(channel_first)).unsqueeze(0)
+    if factor != 1:
+        x = F.interpolate(x, scale_factor=(1.0, float(factor), float(factor)), mode="trilinear", align_corners=False)
+    return x.squeeze(0).numpy()
+
+
+def averaged_foreground(frame_lists, plane_lists, num_frames, threshold, factor=1):
+    """Mean over the sub-clips covering each frame, up-sampled, thresholded (main.py:93-103 with resize_output).
+    Returns (mask bool [T,H,W], mean float64 at output resolution for ambiguity checks)."""
+    import torch
+    import torch.nn.functional as F
+    h, w = plane_lists[0].shape[-2:]
+    acc = np.zeros((num_frames, h, w), np.float32)
+    cnt = np.zeros(num_frames, np.float32)
+    for frames, planes in zip(frame_lists, plane_lists):
+        for j, t in enumerate(frames):
+            acc[t] = acc[t] + planes[j]
+            cnt[t] += 1.0
+    mean = acc / cnt[:, None, None]
+    up = torch.from_numpy(mean).double()[None, None]
+    if factor != 1:
+        up = F.interpolate(up, scale_factor=(1.0, float(factor), float(factor)), mode="trilinear", align_corners=False)
+    up = up[0, 0].numpy()
+    return up > threshold, up

@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -47,6 +47,11 @@ PROTOTYPES = {
     "stemseg_fg_compact": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_fg_compact_threshold": (c_int32, [c_void_p, c_float, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                                c_size_t, c_void_p]),
+    "stemseg_fg_compact_mean_threshold": (c_int32, [c_void_p, c_void_p, c_float, c_int64, c_int32, c_int32, c_int32,
+                                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_frame_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
+    "stemseg_fg_gather_upsampled": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
+                                              c_void_p, c_int32, c_void_p, c_void_p]),
     "stemseg_fg_gather": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                     c_void_p]),
     "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
@@ -90,7 +95,8 @@ _lib = None
 # bench.py reports it as `gpu_launches`
 KERNEL_LAUNCHES = [0]
 KERNELS_PER_CALL = {
-    "stemseg_seq_cluster": 1, "stemseg_fg_compact": 3, "stemseg_fg_compact_threshold": 3, "stemseg_fg_gather": 1,
+    "stemseg_seq_cluster": 1, "stemseg_fg_compact": 3, "stemseg_fg_compact_threshold": 3, "stemseg_fg_gather": 1, "stemseg_fg_compact_mean_threshold": 3, "stemseg_frame_accumulate": 1,
+    "stemseg_fg_gather_upsampled": 1,
     "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                                c_void_p, c_void_p, c_void_p]),
     "stemseg_relabel_lut": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),

@@ -25,6 +25,71 @@ struct ThresholdSrc {
     __device__ __forceinline__ bool operator()(long long i) const { return v[i] > thr; }
 };
 
+// ATen align_corners=False source tap for an integer up-sampling factor (scale = 1 / factor)
+struct Tap1 {
+    int i0, i1;
+    float w0, w1;
+};
+__device__ __forceinline__ Tap1 up_tap(int dst, float inv_factor, int in_size) {
+    float s = __fsub_rn(__fmul_rn(inv_factor, __fadd_rn(static_cast<float>(dst), 0.5f)), 0.5f);
+    if (s < 0.f) s = 0.f;
+    Tap1 t;
+    t.i0 = static_cast<int>(s);
+    if (t.i0 > in_size - 1) t.i0 = in_size - 1;
+    t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+    float lam = __fsub_rn(s, static_cast<float>(t.i0));
+    lam = fminf(fmaxf(lam, 0.f), 1.f);
+    t.w1 = lam;
+    t.w0 = __fsub_rn(1.f, lam);
+    return t;
+}
+// trilinear (1, f, f) interpolation of a [frames][h][w] plane at full-resolution voxel (frame, y, x); transform 1
+// applies exp(v)*10 to the corner values first (the reference resizes the already activated bandwidths)
+__device__ __forceinline__ float sample_up(const float* __restrict__ plane, int h, int w, int factor, int frame, int y,
+                                           int x, int transform) {
+    if (factor == 1) {
+        float v = __ldg(plane + (static_cast<size_t>(frame) * h + y) * w + x);
+        return transform == 1 ? expf(v) * 10.0f : v;
+    }
+    const float inv = 1.0f / static_cast<float>(factor);
+    const Tap1 ty = up_tap(y, inv, h), tx = up_tap(x, inv, w);
+    const float* p = plane + static_cast<size_t>(frame) * h * w;
+    float v00 = __ldg(p + ty.i0 * w + tx.i0), v01 = __ldg(p + ty.i0 * w + tx.i1);
+    float v10 = __ldg(p + ty.i1 * w + tx.i0), v11 = __ldg(p + ty.i1 * w + tx.i1);
+    if (transform == 1) {
+        v00 = expf(v00) * 10.0f; v01 = expf(v01) * 10.0f; v10 = expf(v10) * 10.0f; v11 = expf(v11) * 10.0f;
+    }
+    const float r0 = __fadd_rn(__fmul_rn(tx.w0, v00), __fmul_rn(tx.w1, v01));
+    const float r1 = __fadd_rn(__fmul_rn(tx.w0, v10), __fmul_rn(tx.w1, v11));
+    return __fadd_rn(__fmul_rn(ty.w0, r0), __fmul_rn(ty.w1, r1));
+}
+
+// foreground = up-sampled( sum / count[frame] ) > thr : the seediness (or foreground-logit) average over the sub-clips
+// covering a frame (stemseg/inference/main.py:93-103, inference_model.py:126-128,207), optionally at `factor` x the
+// map resolution (--resize_embeddings, inference_model.py:55-61)
+struct MeanUpThresholdSrc {
+    const float* sum;          // [frames][h][w]
+    const float* count;        // [frames]
+    float thr;
+    int h, w, factor;
+    __device__ __forceinline__ bool operator()(long long i) const {
+        const int W = w * factor, H = h * factor;
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int f = static_cast<int>(i / (1ll * W * H));
+        if (factor == 1) return __fdiv_rn(sum[i], count[f]) > thr;
+        const float inv = 1.0f / static_cast<float>(factor);
+        const Tap1 ty = up_tap(y, inv, h), tx = up_tap(x, inv, w);
+        const float* p = sum + static_cast<size_t>(f) * h * w;
+        const float c = count[f];
+        const float v00 = __fdiv_rn(p[ty.i0 * w + tx.i0], c), v01 = __fdiv_rn(p[ty.i0 * w + tx.i1], c);
+        const float v10 = __fdiv_rn(p[ty.i1 * w + tx.i0], c), v11 = __fdiv_rn(p[ty.i1 * w + tx.i1], c);
+        const float r0 = __fadd_rn(__fmul_rn(tx.w0, v00), __fmul_rn(tx.w1, v01));
+        const float r1 = __fadd_rn(__fmul_rn(tx.w0, v10), __fmul_rn(tx.w1, v11));
+        return __fadd_rn(__fmul_rn(ty.w0, r0), __fmul_rn(ty.w1, r1)) > thr;
+    }
+};
+
 template <class Src>
 __device__ __forceinline__ int count_nonzero_run(const Src& m, long long base, long long begin, long long end) {
     int c = 0;
@@ -140,6 +205,38 @@ __global__ void __launch_bounds__(256) fg_gather_kernel(const float* __restrict_
     }
 }
 
+// gather with on-the-fly (1, f, f) trilinear up-sampling: indices address the FULL-resolution grid [T][f*h][f*w]
+__global__ void __launch_bounds__(256) fg_gather_up_kernel(const float* __restrict__ src, long long channel_stride,
+                                                           int channels, int h, int w, int factor,
+                                                           const int* __restrict__ indices, long long n,
+                                                           const int* __restrict__ n_dev, int transform,
+                                                           float* __restrict__ dst) {
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (n_dev != nullptr && *n_dev < n) n = *n_dev;
+    if (p >= n) return;
+    const long long idx = indices[p];
+    const int W = w * factor, H = h * factor;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int f = static_cast<int>(idx / (1ll * W * H));
+    for (int c = 0; c < channels; ++c)
+        dst[p * channels + c] = sample_up(src + c * channel_stride, h, w, factor, f, y, x, transform);
+}
+
+// dst[frame_ids[j]][..] += src[j][..]; counts[frame_ids[j]] += 1   (per-frame running sums over sub-clips)
+__global__ void __launch_bounds__(256) frame_accumulate_kernel(float* __restrict__ dst, float* __restrict__ counts,
+                                                               const float* __restrict__ src,
+                                                               const int* __restrict__ frame_ids, int frames,
+                                                               long long plane) {
+    const long long total = frames * plane;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+        const int j = static_cast<int>(i / plane);
+        const long long p = i % plane;
+        dst[frame_ids[j] * plane + p] += src[i];
+        if (p == 0) counts[frame_ids[j]] += 1.0f;
+    }
+}
+
 }  // namespace
 }  // namespace stemseg
 
@@ -203,6 +300,44 @@ extern "C" int32_t stemseg_fg_gather(const float* src, int64_t channel_stride, i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
     fg_gather_kernel<<<blocks, 256, 0, stream>>>(src, channel_stride, channels, indices, n, n_dev, transform, dst);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_fg_compact_mean_threshold(const float* sum, const float* count, float threshold,
+                                                     int64_t n_frames, int32_t h, int32_t w, int32_t factor,
+                                                     int32_t* indices, int32_t* frame_counts, void* workspace,
+                                                     size_t workspace_bytes, void* stream_) {
+    SS_REQUIRE(sum && count, "fg_compact_mean_threshold: null input");
+    SS_REQUIRE(h >= 1 && w >= 1 && factor >= 1 && factor <= 8, "fg_compact_mean_threshold: bad shape");
+    MeanUpThresholdSrc src{sum, count, threshold, h, w, factor};
+    return fg_compact_impl(src, n_frames, static_cast<int64_t>(h) * factor * w * factor, indices, frame_counts,
+                           workspace, workspace_bytes, stream_);
+}
+
+extern "C" int32_t stemseg_fg_gather_upsampled(const float* src, int64_t channel_stride, int32_t channels, int32_t h,
+                                               int32_t w, int32_t factor, const int32_t* indices, int64_t n,
+                                               const int32_t* n_dev, int32_t transform, float* dst, void* stream_) {
+    SS_REQUIRE(channels >= 1 && h >= 1 && w >= 1 && factor >= 1 && factor <= 8, "fg_gather_upsampled: bad shape");
+    SS_REQUIRE(transform == 0 || transform == 1, "fg_gather_upsampled: transform must be 0 or 1");
+    if (n == 0) return STEMSEG_OK;
+    SS_REQUIRE(src && indices && dst && n > 0, "fg_gather_upsampled: bad arguments");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    fg_gather_up_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, channel_stride, channels, h, w,
+                                                                                     factor, indices, n, n_dev,
+                                                                                     transform, dst);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_frame_accumulate(float* dst, float* counts, const float* src, const int32_t* frame_ids,
+                                            int32_t frames, int64_t plane, void* stream_) {
+    SS_REQUIRE(dst && counts && src && frame_ids && frames >= 1 && plane >= 1, "frame_accumulate: bad arguments");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    long long blocks = (frames * plane + 255) / 256;
+    const long long cap = 16ll * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    frame_accumulate_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dst, counts, src, frame_ids, frames, plane);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

@@ -120,12 +120,15 @@ def compact_foreground(masks, threshold=None, sync=True):
 
 
 @torch.no_grad()
-def gather_points(channel_first_map, fg_index, transform="none"):
+def gather_points(channel_first_map, fg_index, transform="none", upsample=1):
     """channel_first_map: [C,T,H,W] fp32 CUDA tensor -> [N,C] rows for the foreground voxels (online_chainer.py:265-281)."""
     x = channel_first_map
     code = {"none": 0, "exp10": 1}[transform]        # exp10: bandwidths = exp(v) * 10 (inference_model.py:148)
-    if x.dim() != 4 or tuple(x.shape[1:]) != fg_index.shape:
-        raise ValueError("map shape %s does not match mask shape %s" % (tuple(x.shape), fg_index.shape))
+    expect = fg_index.shape if upsample == 1 else (fg_index.shape[0], fg_index.shape[1] // upsample,
+                                                   fg_index.shape[2] // upsample)
+    if x.dim() != 4 or tuple(x.shape[1:]) != tuple(expect):
+        raise ValueError("map shape %s does not match mask shape %s (upsample %d)" % (
+            tuple(x.shape), fg_index.shape, upsample))
     if x.dtype != torch.float32 or not x.is_cuda:
         raise ValueError("gather_points needs an fp32 CUDA tensor")
     c = x.shape[0]
@@ -140,6 +143,58 @@ def gather_points(channel_first_map, fg_index, transform="none"):
         return out
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c, _lib.ptr(idx), n,
-                                         _lib.ptr(total_dev), code, _lib.ptr(out), _lib.stream_ptr()))
+        if upsample == 1:
+            _lib.check(lib.stemseg_fg_gather(_lib.ptr(x), x.stride(0) if c > 1 else inner, c, _lib.ptr(idx), n,
+                                             _lib.ptr(total_dev), code, _lib.ptr(out), _lib.stream_ptr()))
+        else:   # the (1, s, s) trilinear resize of online_chainer.py:128-140 evaluated only at the foreground voxels
+            _lib.check(lib.stemseg_fg_gather_upsampled(_lib.ptr(x), x.stride(0) if c > 1 else inner, c, x.shape[2],
+                                                       x.shape[3], int(upsample), _lib.ptr(idx), n,
+                                                       _lib.ptr(total_dev), code, _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+class FrameAverager(object):
+    """Per-frame running mean of a map over the sub-clips that cover the frame, kept on the device.
+
+    The reference averages the seediness maps (stemseg/inference/main.py:93-103) or the foreground logits
+    (inference_model.py:126-128,207) of overlapping sub-clips on the host, frame by frame; here each sub-clip adds its
+    [T',h,w] planes into [T,h,w] sums and ``foreground_index`` thresholds mean (optionally up-sampled x4) inside the
+    compaction kernel."""
+
+    def __init__(self, num_frames, height, width, device):
+        self.device = torch.device(device)
+        self.sum = torch.zeros((num_frames, height, width), dtype=torch.float32, device=self.device)
+        self.count = torch.zeros(num_frames, dtype=torch.float32, device=self.device)
+
+    @torch.no_grad()
+    def add(self, frames, planes):
+        """planes: [len(frames), h, w] fp32 CUDA tensor (e.g. seediness[0] of one sub-clip)."""
+        if tuple(planes.shape) != (len(frames),) + tuple(self.sum.shape[1:]):
+            raise ValueError("planes %s do not match %d frames of %s" % (tuple(planes.shape), len(frames),
+                                                                          tuple(self.sum.shape[1:])))
+        lib = _lib.load()
+        planes = planes.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            ids = torch.tensor(list(frames), dtype=torch.int32, device=self.device)
+            _lib.check(lib.stemseg_frame_accumulate(_lib.ptr(self.sum), _lib.ptr(self.count), _lib.ptr(planes),
+                                                    _lib.ptr(ids), len(frames), self.sum.shape[1] * self.sum.shape[2],
+                                                    _lib.stream_ptr()))
+
+    @torch.no_grad()
+    def foreground_index(self, threshold, upsample=1, sync=True):
+        """ForegroundIndex of ``upsample(mean) > threshold`` on the [T, s*h, s*w] grid."""
+        lib = _lib.load()
+        t, h, w = self.sum.shape
+        s = int(upsample)
+        with torch.cuda.device(self.device):
+            ws_bytes = lib.stemseg_fg_compact_workspace_bytes(t, h * s * w * s)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            indices = torch.empty(t * h * s * w * s, dtype=torch.int32, device=self.device)
+            counts = torch.empty(t + 1, dtype=torch.int32, device=self.device)
+            _lib.check(lib.stemseg_fg_compact_mean_threshold(_lib.ptr(self.sum), _lib.ptr(self.count), float(threshold),
+                                                             t, h, w, s, _lib.ptr(indices), _lib.ptr(counts),
+                                                             _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+            if not sync:
+                return ForegroundIndex(indices, None, (t, h * s, w * s), counts_dev=counts)
+            counts_host = counts.cpu().tolist()
+        return ForegroundIndex(indices[:counts_host[-1]], counts_host[:-1], (t, h * s, w * s))

@@ -57,3 +57,45 @@ def test_gather_strided_view(cuda_device):
         got = gather_points(dev[sl], fg)
         exp = go.gather_map(coords, full[sl])
         np.testing.assert_array_equal(got.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("factor", [1, 2, 4])
+def test_upsampled_gather_matches_resized_maps(factor, cuda_device):
+    """gather with the fused (1,s,s) trilinear resize == resize the maps (torch CPU), then gather."""
+    from stemseg_b200.foreground import compact_foreground, gather_points
+    rng = np.random.default_rng(factor)
+    t, h, w = 4, 12, 20
+    emb = rng.standard_normal((4, t, h, w)).astype(np.float32)
+    var = rng.uniform(-1, 1, size=(2, t, h, w)).astype(np.float32)
+    mask = rng.random((t, h * factor, w * factor)) < 0.3
+    coords, _ = go.masks_to_coord_list(mask)
+    fg = compact_foreground(torch.from_numpy(mask).to(cuda_device))
+    got = gather_points(torch.from_numpy(emb).to(cuda_device), fg, upsample=factor).cpu().numpy()
+    exp = go.gather_map(coords, go.resize_map(emb, factor))
+    np.testing.assert_allclose(got, exp, rtol=2e-6, atol=2e-6)          # fp32 interpolation (FMA-order differences)
+    got_bw = gather_points(torch.from_numpy(var).to(cuda_device), fg, transform="exp10", upsample=factor).cpu().numpy()
+    exp_bw = go.gather_map(coords, go.resize_map((np.exp(var) * 10.0).astype(np.float32), factor))
+    np.testing.assert_allclose(got_bw, exp_bw, rtol=5e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("factor", [1, 4])
+def test_frame_averager_foreground(factor, cuda_device):
+    """Seediness averaged over overlapping sub-clips, (up-sampled,) thresholded inside the compaction kernel."""
+    from stemseg_b200.foreground import FrameAverager
+    rng = np.random.default_rng(10 + factor)
+    num_frames, h, w = 12, 24, 32
+    frame_lists = [list(range(0, 8)), list(range(4, 12)), [0, 0, 3, 5, 7, 9, 10, 11][:8]]
+    frame_lists[2] = sorted(set(frame_lists[2]))
+    planes = [rng.random((len(f), h, w)).astype(np.float32) for f in frame_lists]
+    avg = FrameAverager(num_frames, h, w, cuda_device)
+    for f, p in zip(frame_lists, planes):
+        avg.add(f, torch.from_numpy(p).to(cuda_device))
+    fg = avg.foreground_index(0.45, upsample=factor)
+    mask, mean = go.averaged_foreground(frame_lists, planes, num_frames, 0.45, factor)
+    got = torch.zeros(mask.size, dtype=torch.bool)
+    got[fg.indices.long().cpu()] = True
+    got = got.view(*mask.shape).numpy()
+    ambiguous = np.abs(mean - 0.45) < 1e-6            # fp32 rounding can flip values sitting on the threshold
+    assert ((got == mask) | ambiguous).all()
+    assert ambiguous.sum() < 10
+    assert fg.shape == mask.shape and sum(fg.frame_counts) == fg.num_points
