@@ -193,18 +193,20 @@ class OnlineChainer(object):
     def __init__(self, clusterer, embedding_resize_factor):
         self.clusterer = clusterer
         self.resize_scale = embedding_resize_factor
-        if embedding_resize_factor != 1.0:
-            raise NotImplementedError("embedding_resize_factor != 1.0 (full-resolution clustering, online_chainer.py:"
-                                      "128-140) is a 'next' row (SURVEY.md §8f-4)")
+        if float(embedding_resize_factor) != int(embedding_resize_factor) or not 1 <= int(embedding_resize_factor) <= 8:
+            raise NotImplementedError("embedding_resize_factor must be an integer in [1, 8] (the reference uses 1 or 4)")
+        # resize_tensors (online_chainer.py:128-140) is never materialised: the (1, s, s) trilinear interpolation is
+        # evaluated by the gather kernel at the foreground voxels of the full-resolution mask only
+        self._upsample = int(embedding_resize_factor)
 
     @torch.no_grad()
     def cluster_subsequence(self, mask_idxes, embeddings, bandwidths, seediness, label_start, return_fg_embeddings):
         """mask_idxes: ForegroundIndex of the sub-clip's frames (see ``process``); maps are [C,T,H,W] CUDA tensors.
         Returns (per-frame label list, [N,E] foreground embeddings, clustering meta) (online_chainer.py:244-289)."""
         assert len(mask_idxes.frame_counts) == embeddings.shape[1]
-        emb_flat = gather_points(embeddings, mask_idxes)
-        bw_flat = gather_points(bandwidths, mask_idxes)
-        seed_flat = gather_points(seediness, mask_idxes)
+        emb_flat = gather_points(embeddings, mask_idxes, upsample=self._upsample)
+        bw_flat = gather_points(bandwidths, mask_idxes, upsample=self._upsample)
+        seed_flat = gather_points(seediness, mask_idxes, upsample=self._upsample)
         labels, meta = self.clusterer(emb_flat, bandwidths=bw_flat, seediness=seed_flat,
                                       cluster_label_start=label_start, return_label_masks=return_fg_embeddings)
         assert labels.numel() == emb_flat.shape[0]
@@ -224,8 +226,8 @@ class OnlineChainer(object):
                 subseq['frames'] = sorted(subseq['frames'].keys())
             frames = list(subseq['frames'])
             emb = subseq['embeddings'].to(device)
-            assert emb.shape[-2:] == masks.shape[-2:], \
-                "Size mismatch between embeddings {} and masks {}".format(emb.shape, masks.shape)
+            assert (emb.shape[-2] * self._upsample, emb.shape[-1] * self._upsample) == tuple(masks.shape[-2:]), \
+                "Size mismatch between embeddings {} (x{}) and masks {}".format(emb.shape, self._upsample, masks.shape)
             labels, fg_emb, meta = self.cluster_subsequence(
                 fg_all.frame_slice(frames), emb, subseq['bandwidths'].to(device), subseq['seediness'].to(device), 1,
                 return_fg_embeddings)

@@ -63,3 +63,29 @@ def test_device_stitch_matches_reference(name, golden_dir, cuda_device):
         np.testing.assert_array_equal(labs.cpu().numpy().astype(np.int32), golden["%s/subseq/%d" % (name, i)])
     flat = sum([m["instance_labels"] + [-999] for m in meta_out], [])
     assert flat == golden[name + "/instance_labels"].tolist()
+
+
+def test_full_resolution_clustering(cuda_device):
+    """embedding_resize_factor = 2: maps stay at low resolution, the mask is at 2x; the fused gather evaluates the
+    trilinear resize at the foreground voxels; clustering is bit-exact against the oracle on the gathered points."""
+    from oracle import cluster_oracle as co
+    from stemseg_b200.chaining import OnlineChainer
+    from stemseg_b200.clusterers import SequentialClustering
+    from stemseg_b200.foreground import compact_foreground, gather_points
+    masks, subseqs = make_video(**CASES["three_blobs"])
+    s = subseqs[0]
+    up = 2
+    big = np.repeat(np.repeat(masks[s["frames"]], up, axis=1), up, axis=2)
+    chainer = OnlineChainer(SequentialClustering(0.5, 0.3, 0.5, 2, [0.3, 0.3], cuda_device), float(up))
+    emb, bw, sd = [torch.from_numpy(s[k]).to(cuda_device) for k in ("embeddings", "bandwidths", "seediness")]
+    fg = compact_foreground(torch.from_numpy(big).to(cuda_device))
+    labels, emb_flat, meta = chainer.cluster_subsequence(fg, emb, bw, sd, 5, False)
+    assert [l.numel() for l in labels] == fg.frame_counts and emb_flat.shape == (fg.num_points, 4)
+    e = emb_flat.cpu().numpy()
+    b = gather_points(bw, fg, upsample=up).cpu().numpy()
+    d = gather_points(sd, fg, upsample=up).cpu().numpy()
+    o_labels, o_meta = co.sequential_cluster(e, b, d, 0.5, 0.3, 0.5, 2, [0.3, 0.3], cluster_label_start=5)
+    np.testing.assert_array_equal(torch.cat(labels).cpu().numpy(), o_labels)
+    assert meta["instance_labels"] == o_meta["instance_labels"]
+    with pytest.raises(NotImplementedError):
+        OnlineChainer(chainer.clusterer, 1.5)
