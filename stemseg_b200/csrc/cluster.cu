@@ -139,11 +139,18 @@ __device__ __forceinline__ void publish_key(unsigned long long key, unsigned lon
     }
 }
 
-template <int E, bool VEC>
-__global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
+constexpr int kUnroll = 4;      // independent points in flight per thread in the streaming variant
+
+// R > 0: register-resident variant -- every thread keeps its (<= R) points (embedding, key, state) in registers for the
+// whole call, so an iteration touches no global memory besides the winner slot: pure grid-barrier latency.  Used
+// when N <= gridDim * kThreads * R (quarter-resolution point sets).  R == 0: streaming variant for large N
+// (full-resolution clustering): kUnroll independent points per loop trip keep enough loads in flight.
+template <int E, bool VEC, int R>
+__global__ void __launch_bounds__(kThreads) seq_cluster_kernel(const ClusterArgs a) {
+    long long n = a.n;
     if (a.n_dev != nullptr) {
         const long long nd = *a.n_dev;
-        if (nd < a.n) a.n = nd;
+        if (nd < n) n = nd;
     }
     __shared__ float s_center[kMaxI][E];
     __shared__ float s_bw[kMaxI][E];
@@ -151,14 +158,32 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
 
     const long long tid0 = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    constexpr int RR = R > 0 ? R : 1;
+    float rx[RR][E];                      // resident points
+    unsigned long long rkey[RR];          // their argmax keys (0 = not a valid point)
+    int rst[RR];                          // -1 unassigned, else ordinal of the claiming cluster
 
     // pass 0: all points are unassigned (clusterers.py:96); winner of iteration 0
     {
         unsigned long long key = 0ull;
-        for (long long idx = tid0; idx < a.n; idx += stride) {
-            a.primary[idx] = -1;
-            const unsigned long long k = make_key(__ldg(a.seed + idx), static_cast<unsigned int>(idx));
-            key = k > key ? k : key;
+        if (R > 0) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                const long long idx = tid0 + r * stride;
+                rkey[r] = 0ull;
+                rst[r] = -1;
+                if (idx < n) {
+                    load_point<E, VEC>(a.emb, idx, rx[r]);
+                    rkey[r] = make_key(__ldg(a.seed + idx), static_cast<unsigned int>(idx));
+                    key = rkey[r] > key ? rkey[r] : key;
+                }
+            }
+        } else {
+            for (long long idx = tid0; idx < n; idx += stride) {
+                a.primary[idx] = -1;
+                const unsigned long long k = make_key(__ldg(a.seed + idx), static_cast<unsigned int>(idx));
+                key = k > key ? k : key;
+            }
         }
         publish_key(key, a.best + 0, s_red);
     }
@@ -187,16 +212,46 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
         for (int k = 0; k < E; ++k) { c[k] = s_center[i][k]; b[k] = s_bw[i][k]; }
 
         unsigned long long key = 0ull;
-        for (long long idx = tid0; idx < a.n; idx += stride) {
-            if (a.primary[idx] != -1) continue;                             // clusterers.py:107
-            float x[E];
-            load_point<E, VEC>(a.emb, idx, x);
-            const float d = mahalanobis<E>(x, c, b);                        // clusterers.py:129-130
-            if (d <= a.d1) {                                                // clusterers.py:136-143
-                a.primary[idx] = i;
-            } else {
-                const unsigned long long k = make_key(__ldg(a.seed + idx), static_cast<unsigned int>(idx));
-                key = k > key ? k : key;
+        if (R > 0) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                if (rkey[r] != 0ull && rst[r] == -1) {                      // clusterers.py:107
+                    const float d = mahalanobis<E>(rx[r], c, b);            // clusterers.py:129-130
+                    if (d <= a.d1) rst[r] = i;                              // clusterers.py:136-143
+                    else key = rkey[r] > key ? rkey[r] : key;
+                }
+            }
+        } else {
+            for (long long idx0 = tid0; idx0 < n; idx0 += stride * kUnroll) {
+                int st[kUnroll];
+                float x[kUnroll][E];
+                float sd[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const long long idx = idx0 + u * stride;
+                    st[u] = idx < n ? a.primary[idx] : 0;                 // clusterers.py:107
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const long long idx = idx0 + u * stride;
+                    if (st[u] == -1) {
+                        load_point<E, VEC>(a.emb, idx, x[u]);
+                        sd[u] = __ldg(a.seed + idx);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const long long idx = idx0 + u * stride;
+                    if (st[u] == -1) {
+                        const float d = mahalanobis<E>(x[u], c, b);         // clusterers.py:129-130
+                        if (d <= a.d1) {                                    // clusterers.py:136-143
+                            a.primary[idx] = i;
+                        } else {
+                            const unsigned long long k = make_key(sd[u], static_cast<unsigned int>(idx));
+                            key = k > key ? k : key;
+                        }
+                    }
+                }
             }
         }
         if (i + 1 < a.max_inst) {
@@ -211,13 +266,10 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
     // loop ran out.  Such points were available in every iteration, so all their K distances are real.
     const bool exhausted = exit_reason == 0;
     const bool do_secondary = num_clusters >= 1 && exit_reason != 1;
-    for (long long idx = tid0; idx < a.n; idx += stride) {
-        const int pl = a.primary[idx];
+    auto finish_point = [&](long long idx, int pl, const float (&x)[E]) {
         long long out = pl < 0 ? -1ll : static_cast<long long>(pl) + a.label_start;
         const bool avail = pl < 0 || (exhausted && pl == a.max_inst - 1);
         if (do_secondary && avail) {
-            float x[E];
-            load_point<E, VEC>(a.emb, idx, x);
             float dmax = 0.f;
             int kmax = 0;
             bool has_nan = false;
@@ -229,13 +281,31 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
             if (!has_nan && dmax <= a.d2) out = static_cast<long long>(kmax) + a.label_start;
         }
         a.labels[idx] = out;
+    };
+    if (R > 0) {
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            const long long idx = tid0 + r * stride;
+            if (idx < n) {
+                a.primary[idx] = rst[r];
+                finish_point(idx, rst[r], rx[r]);
+            }
+        }
+    } else {
+        for (long long idx = tid0; idx < n; idx += stride) {
+            const int pl = a.primary[idx];
+            const bool avail = pl < 0 || (exhausted && pl == a.max_inst - 1);
+            float x[E];
+            if (do_secondary && avail) load_point<E, VEC>(a.emb, idx, x);
+            finish_point(idx, pl, x);
+        }
     }
 
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
             a.meta[0] = static_cast<unsigned int>(num_clusters);
             a.meta[1] = static_cast<unsigned int>(exit_reason);
-            a.meta[2] = static_cast<unsigned int>(a.n);      // points actually clustered
+            a.meta[2] = static_cast<unsigned int>(n);      // points actually clustered
             a.meta[3] = 0u;
         }
         float* centers = reinterpret_cast<float*>(a.meta + 4 + a.max_inst);
@@ -247,23 +317,48 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(ClusterArgs a) {
     }
 }
 
+template <int E, bool VEC, int R>
+int launch_cluster_r(const ClusterArgs& args, long long blocks, cudaStream_t stream) {
+    auto kernel = seq_cluster_kernel<E, VEC, R>;
+    int per_sm = 0;
+    SS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    const long long resident = static_cast<long long>(per_sm) * device_sm_count();
+    if (per_sm < 1 || blocks > resident) {
+        set_error("seq_cluster: %lld blocks cannot be co-resident (%lld fit)", blocks, resident);
+        return STEMSEG_ERR_CUDA;
+    }
+    void* kargs[] = {const_cast<ClusterArgs*>(&args)};
+    SS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(static_cast<unsigned>(blocks)),
+                                           dim3(kThreads), kargs, 0, stream));
+    return STEMSEG_OK;
+}
+
 template <int E, bool VEC>
 int launch_cluster(const ClusterArgs& args, cudaStream_t stream) {
-    auto kernel = seq_cluster_kernel<E, VEC>;
+    const long long sms = device_sm_count();
+    const long long per_block = kThreads;
+    // register-resident variants: as few blocks as possible (cheap grid barrier), at most one per SM if R <= 4 allows
+    for (int r : {1, 2, 4}) {
+        const long long blocks = (args.n + per_block * r - 1) / (per_block * r);
+        if (blocks <= sms || (r == 4 && blocks <= 2 * sms)) {
+            const long long b = blocks < 1 ? 1 : blocks;
+            if (r == 1) return launch_cluster_r<E, VEC, 1>(args, b, stream);
+            if (r == 2) return launch_cluster_r<E, VEC, 2>(args, b, stream);
+            return launch_cluster_r<E, VEC, 4>(args, b, stream);
+        }
+    }
+    // streaming variant: fill the device
+    auto kernel = seq_cluster_kernel<E, VEC, 0>;
     int per_sm = 0;
     SS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
     if (per_sm < 1) {
         set_error("seq_cluster: kernel does not fit on an SM");
         return STEMSEG_ERR_CUDA;
     }
-    long long blocks = (args.n + kThreads - 1) / kThreads;
-    const long long resident = static_cast<long long>(per_sm) * device_sm_count();
-    if (blocks > resident) blocks = resident;
-    if (blocks < 1) blocks = 1;
-    void* kargs[] = {const_cast<ClusterArgs*>(&args)};
-    SS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(static_cast<unsigned>(blocks)),
-                                           dim3(kThreads), kargs, 0, stream));
-    return STEMSEG_OK;
+    long long blocks = static_cast<long long>(per_sm) * sms;
+    const long long need = (args.n + per_block - 1) / per_block;
+    if (blocks > need) blocks = need;
+    return launch_cluster_r<E, VEC, 0>(args, blocks, stream);
 }
 
 template <int E>
