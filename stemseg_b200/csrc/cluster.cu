@@ -333,31 +333,29 @@ int launch_cluster_r(const ClusterArgs& args, long long blocks, cudaStream_t str
     return STEMSEG_OK;
 }
 
+template <int E, bool VEC, int R>
+long long resident_blocks() {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seq_cluster_kernel<E, VEC, R>, kThreads, 0) != cudaSuccess)
+        return 0;
+    return static_cast<long long>(per_sm) * device_sm_count();
+}
+
 template <int E, bool VEC>
 int launch_cluster(const ClusterArgs& args, cudaStream_t stream) {
-    const long long sms = device_sm_count();
     const long long per_block = kThreads;
-    // register-resident variants: as few blocks as possible (cheap grid barrier), at most one per SM if R <= 4 allows
-    for (int r : {1, 2, 4}) {
-        const long long blocks = (args.n + per_block * r - 1) / (per_block * r);
-        if (blocks <= sms || (r == 4 && blocks <= 2 * sms)) {
-            const long long b = blocks < 1 ? 1 : blocks;
-            if (r == 1) return launch_cluster_r<E, VEC, 1>(args, b, stream);
-            if (r == 2) return launch_cluster_r<E, VEC, 2>(args, b, stream);
-            return launch_cluster_r<E, VEC, 4>(args, b, stream);
-        }
-    }
+    auto blocks_for = [&](int r) { return (args.n + per_block * r - 1) / (per_block * r); };
+    // register-resident variants, fewest blocks first (cheapest grid barrier), if all blocks can be co-resident
+    if (blocks_for(4) <= resident_blocks<E, VEC, 4>()) return launch_cluster_r<E, VEC, 4>(args, blocks_for(4), stream);
+    if (blocks_for(2) <= resident_blocks<E, VEC, 2>()) return launch_cluster_r<E, VEC, 2>(args, blocks_for(2), stream);
+    if (blocks_for(1) <= resident_blocks<E, VEC, 1>()) return launch_cluster_r<E, VEC, 1>(args, blocks_for(1), stream);
     // streaming variant: fill the device
-    auto kernel = seq_cluster_kernel<E, VEC, 0>;
-    int per_sm = 0;
-    SS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-    if (per_sm < 1) {
+    long long blocks = resident_blocks<E, VEC, 0>();
+    if (blocks < 1) {
         set_error("seq_cluster: kernel does not fit on an SM");
         return STEMSEG_ERR_CUDA;
     }
-    long long blocks = static_cast<long long>(per_sm) * sms;
-    const long long need = (args.n + per_block - 1) / per_block;
-    if (blocks > need) blocks = need;
+    if (blocks > blocks_for(1)) blocks = blocks_for(1);
     return launch_cluster_r<E, VEC, 0>(args, blocks, stream);
 }
 
