@@ -203,14 +203,17 @@ int32_t stemseg_conv3d_tiles_per_sample(const StemsegConvShape* shape);
 size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
 int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_t slices, int32_t n, int64_t spatial, int32_t c,
                                  int32_t channels_per_group, float eps, const float* gamma, const float* beta,
-                                 float* scale_shift, void* workspace, size_t workspace_bytes, void* stream);
+                                 float* scale_shift, float* mean_rstd, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+/* mean_rstd (optional, [n][c/channels_per_group][2]): the group statistics themselves, saved for the backward pass */
 
 /* Second half of stemseg_group_norm_stats for partial sums produced elsewhere (the conv epilogue): `partial` points
  * at channel 0 of the c channels to normalise inside a [n][c_total][chunks][2] buffer, partial_sample_stride =
  * c_total*chunks*2 floats. */
 int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample_stride, int32_t chunks, int32_t n,
                                     int64_t spatial, int32_t c, int32_t channels_per_group, float eps,
-                                    const float* gamma, const float* beta, float* scale_shift, void* stream);
+                                    const float* gamma, const float* beta, float* scale_shift, float* mean_rstd,
+                                    void* stream);
 
 /* relu(x * scale + shift) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
  * (embedding_decoder.py:22-24; common.py:8-24).  scale_shift NULL = no normalisation (NormType Identity). */
@@ -272,6 +275,57 @@ int32_t stemseg_rank_map_scatter(const int32_t* indices, const int64_t* labels, 
                                  int32_t nlut, uint8_t* rank_map, int64_t map_elems, void* stream);
 int32_t stemseg_mask_writeback(const uint8_t* rank_map, int32_t frames, int32_t h, int32_t w, int32_t upscale,
                                int32_t crop_h, int32_t crop_w, int32_t out_h, int32_t out_w, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward pass of the decoder heads (the reference relies on torch autograd through
+ * nn.Conv3d / nn.GroupNorm / nn.AvgPool3d / F.interpolate, stemseg/training/main.py:188-201).
+ * GEMM-shaped parts reuse the tcgen05 convolution kernel:
+ *   dgrad  = stemseg_conv3d_bf16_planes(dy planes, weights packed by stemseg_pack_conv_weight_dgrad);
+ *   wgrad  = stemseg_conv3d_wgrad on zero-padded TRANSPOSED planes (stemseg_transpose_pad), 27 K-major GEMMs whose B
+ *            operand is read at the constant offset of the tap, followed by stemseg_wgrad_reduce.
+ * Batch size 1 per call (the reference trains with MAX_SAMPLES_PER_GPU = 1, defaults.yaml:20).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* W'[ci][taps-1-tap][co] = W[co][cin_begin+ci][tap] as K-major bf16 planes (rows = ci, K = taps*cout) */
+int32_t stemseg_pack_conv_weight_dgrad(const float* src, int32_t cout, int32_t cin_total, int32_t cin_begin,
+                                       int32_t cin_count, int32_t taps, void* dst_planes, int32_t planes, void* stream);
+/* output heads: given grad_out [n][n_out][t][h][w] -> dx [n][t][h][w][c] (x = z + up(y_low)), d_weight [n_out][c],
+ * d_bias [n_out] */
+size_t stemseg_head_backward_workspace_bytes(int32_t c);
+int32_t stemseg_head_backward(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                              int32_t t_scale, const float* out_weight, const float* out_bias,
+                              const int32_t* activation, int32_t n_out, const float* grad_out, float* dx,
+                              float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+/* adjoint of the trilinear (t_scale, 2, 2) up-sampling: d_low [n][t/t_scale][h/2][w/2][c] from d_high [n][t][h][w][c] */
+int32_t stemseg_upsample_transpose(const float* d_high, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                                   int32_t t_scale, float* d_low, void* stream);
+/* AvgPool3d(3,(2,1,1),1) (if pool) + ReLU backward: d_norm [n][t][h][w][c] from d_out [n][t_out][h][w][c] */
+int32_t stemseg_pool_relu_backward(const float* d_out, const float* y, const float* scale_shift, int32_t n, int32_t t,
+                                   int32_t h, int32_t w, int32_t c, int32_t pool, float* d_norm, void* stream);
+/* GroupNorm backward: d_norm_to_dy is overwritten with dy; dgamma_dbeta [n][c][2]; group_terms [n][groups][2] scratch */
+size_t stemseg_group_norm_backward_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
+int32_t stemseg_group_norm_backward(float* d_norm_to_dy, const float* y, const float* mean_rstd, const float* gamma,
+                                    int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
+                                    float* dgamma_dbeta, float* group_terms, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+/* out[c] = sum over rows of x[rows][c] (bias gradients), deterministic */
+size_t stemseg_channel_sum_workspace_bytes(int64_t rows, int32_t c);
+int32_t stemseg_channel_sum(const float* x, int64_t rows, int32_t c, float* out, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* fp32 -> bf16 planes without activation (gradients entering a dgrad GEMM) */
+int32_t stemseg_to_planes(const float* x, int64_t elems, void* dst_planes, int32_t planes, void* stream);
+/* [t*h*w][c] (fp32, or bf16 planes when src_is_planes) -> zero-padded transposed bf16 planes [P][c][row_length] with
+ * row_length = stemseg_transposed_row_length(t, h, w, pad) and element (t,y,x) at ((t+pad)(h+2pad)+(y+pad))(w+2pad)+x+pad */
+int64_t stemseg_transposed_row_length(int32_t t, int32_t h, int32_t w, int32_t pad);
+int32_t stemseg_transpose_pad(const void* src, int32_t src_is_planes, int32_t t, int32_t h, int32_t w, int32_t c,
+                              int32_t pad, void* dst_planes, int32_t planes, void* stream);
+/* slices [k_splits][taps][cout][cin] fp32 partial weight gradients; see the section comment */
+int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t kernel_size);
+int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_planes, int32_t cout, int32_t cin, int32_t t,
+                             int32_t h, int32_t w, int32_t kernel_size, int32_t planes, int32_t k_splits, float* slices,
+                             void* stream);
+/* sum the slices into the state_dict layout dst[cout][cin_total][taps] at input-channel offset cin_begin */
+int32_t stemseg_wgrad_reduce(const float* slices, int32_t n_slices, int32_t cout, int32_t ntaps, int32_t cin, float* dst,
+                             int32_t cin_total, int32_t cin_begin, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

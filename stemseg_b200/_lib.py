@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -68,11 +68,35 @@ PROTOTYPES = {
                                              ctypes.POINTER(StemsegConvShape), c_int32, c_void_p]),
     "stemseg_conv3d_tiles_per_sample": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_finalize": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_int32, c_float,
-                                              c_void_p, c_void_p, c_void_p, c_void_p]),
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "stemseg_pack_conv_weight_dgrad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                                 c_int32, c_void_p]),
+    "stemseg_head_backward_workspace_bytes": (c_size_t, [c_int32]),
+    "stemseg_head_backward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "stemseg_upsample_transpose": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                             c_void_p]),
+    "stemseg_pool_relu_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                             c_int32, c_void_p, c_void_p]),
+    "stemseg_group_norm_backward_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "stemseg_group_norm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
+                                              c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_channel_sum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "stemseg_channel_sum": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_to_planes": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
+    "stemseg_transposed_row_length": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "stemseg_transpose_pad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                        c_int32, c_void_p]),
+    "stemseg_wgrad_k_splits": (c_int32, [c_int32, c_int32, c_int32]),
+    "stemseg_conv3d_wgrad": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_int32, c_int32, c_void_p, c_void_p]),
+    "stemseg_wgrad_reduce": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                                       c_int32, c_void_p]),
     "stemseg_conv3d_auto_split": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_float,
-                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "stemseg_upsample_add": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
@@ -108,6 +132,9 @@ KERNELS_PER_CALL = {
     "stemseg_head_lowres": 1, "stemseg_conv1x1_head_output": 1,
     "stemseg_label_pair_histogram": 1, "stemseg_relabel_lut": 1,
     "stemseg_rank_map_scatter": 1, "stemseg_mask_writeback": 1,
+    "stemseg_pack_conv_weight_dgrad": 1, "stemseg_head_backward": 3, "stemseg_upsample_transpose": 1,
+    "stemseg_pool_relu_backward": 1, "stemseg_group_norm_backward": 3, "stemseg_channel_sum": 2,
+    "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
 }
 
 

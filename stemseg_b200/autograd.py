@@ -1,0 +1,251 @@
+"""Training support: autograd through the B200 decoder heads.
+
+The reference trains its heads through torch autograd over nn.Conv3d / nn.GroupNorm / nn.AvgPool3d / F.interpolate
+(stemseg/training/main.py:188-201 -> model_builder.py:171-208).  Here the forward is the CUDA plan of
+stemseg_b200/decoder.py run eagerly with its intermediates kept, and the backward is hand-written:
+
+  * dgrad of every convolution = the tcgen05 convolution kernel itself on the gradient planes with flipped /
+    transposed weights (``stemseg_pack_conv_weight_dgrad``);
+  * wgrad = the same kernel in GEMM mode on zero-padded transposed planes (``stemseg_conv3d_wgrad``);
+  * output heads, trilinear adjoint, AvgPool/ReLU and GroupNorm backward: csrc/backward_ops.cu.
+
+Gradients flow to the four feature maps (so the torch backbone trains as usual) and to every head parameter, which is
+all DistributedDataParallel needs: its gradient all-reduce hooks fire on the parameters' ``.grad`` as with the
+reference heads.  One sub-clip per call (batch 1), like the reference's MAX_SAMPLES_PER_GPU = 1 (defaults.yaml:20).
+"""
+import torch
+
+from stemseg_b200 import _lib
+from stemseg_b200 import decoder as D
+
+
+def _check(rc):
+    _lib.check(rc)
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def training_forward(head, feats):
+    """Eager forward keeping what the backward needs.  Returns (out, saved)."""
+    spec = head.head_spec()
+    weights, out_spec = spec.weights, spec.out_spec
+    planes = D.PRECISION_PLANES[head.precision]
+    pools, tscale = D.pool_schedule(head.num_frames)
+    has_norm = head._has_norm
+    saved = {"blocks": {}, "merges": [], "planes": planes, "tscale": tscale}
+    D.KEEP = []
+    branch = []
+    for (name, n_stages), feat in zip(D.BLOCKS, feats):
+        if feat.shape[0] != 1:
+            raise NotImplementedError("training through the B200 heads handles one sub-clip per call (batch 1)")
+        a = D.pack_activation(feat, planes)
+        stages = []
+        for j in range(n_stages):
+            conv, gamma, beta = weights.stages[name][j]
+            y = D.conv3d(a, conv, allow_split=has_norm)
+            st = {}
+            pool = bool(pools[j] and name != "block_4x")
+            a_next = D.group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps, pool, planes, saved=st)
+            y0 = y[0] if y.dim() == 6 else y            # the statistics pass summed split-K slices into slice 0
+            stages.append({"a_in": a, "y": y0, "scale_shift": st.get("scale_shift"), "mean_rstd": st.get("mean_rstd"),
+                           "pool": pool, "gamma": gamma, "conv": conv})
+            a = a_next
+        saved["blocks"][name] = stages
+        branch.append(a)
+    x = branch[0]
+    out = None
+    for k in range(3):
+        w_up, w_skip = weights.merges[k]
+        y_low = D.conv3d(x, w_up)
+        z = D.conv3d(branch[k + 1], w_skip)
+        saved["merges"].append({"x_in": x, "f_in": branch[k + 1], "y_low": y_low, "z": z})
+        if k < 2:
+            x = D.upsample_add(z, y_low, tscale[k], planes)
+        else:
+            out = D.head_output(z, y_low, tscale[k], out_spec)
+    saved["out_spec"] = out_spec
+    D.KEEP = []
+    return out, saved
+
+
+def _dgrad_weights(head):
+    """Flipped / transposed packed weights of every convolution (cached per parameter version)."""
+    key = head._cache_key()
+    cache = getattr(head, "_dgrad_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    lib = _lib.load()
+    planes = D.PRECISION_PLANES[head.precision]
+    params = dict(head.named_parameters())
+    packed = {}
+
+    def pack(wname, cin_begin, cin_count):
+        w = params[wname].detach().contiguous()
+        cout, cin_total = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3] * w.shape[4]
+        dst = _empty((planes, cin_count, taps * cout), torch.bfloat16, w.device)
+        _check(lib.stemseg_pack_conv_weight_dgrad(_lib.ptr(w), cout, cin_total, cin_begin, cin_count, taps,
+                                                  _lib.ptr(dst), planes, _lib.stream_ptr()))
+        return D.PackedConv(dst, None, cout, cin_count, 3 if taps == 27 else 1)
+
+    with torch.cuda.device(next(head.parameters()).device):
+        for name, n_stages in D.BLOCKS:
+            for j in range(n_stages):
+                wname = "%s.%d.weight" % (name, 4 * j)
+                packed[wname] = pack(wname, 0, params[wname].shape[1])
+        c = head.inter_channels
+        for k, merge in enumerate(D.MERGES):
+            packed[(merge, "up")] = pack(merge + ".weight", 0, c[k])
+            packed[(merge, "skip")] = pack(merge + ".weight", c[k], c[k + 1])
+    head._dgrad_cache = (key, packed)
+    return packed
+
+
+def _to_planes(x, planes):
+    """fp32 NDHWC [1,t,h,w,c] -> Planes (no activation)."""
+    lib = _lib.load()
+    n, t, h, w, c = x.shape
+    dst = _empty((planes, n, t, h, w, c), torch.bfloat16, x.device)
+    _check(lib.stemseg_to_planes(_lib.ptr(x), x.numel(), _lib.ptr(dst), planes, _lib.stream_ptr()))
+    return D.Planes(dst, n, t, h, w, c)
+
+
+def _wgrad(dy, x_planes, kernel_size, planes, dst, cin_begin):
+    """dst[cout][cin_total][taps] (a parameter gradient in state_dict layout) <- wgrad(dy fp32 NDHWC, x Planes)."""
+    lib = _lib.load()
+    _, t, h, w, co = dy.shape
+    ci = x_planes.c
+    assert (x_planes.t, x_planes.h, x_planes.w) == (t, h, w)
+    pad = 1 if kernel_size == 3 else 0
+    taps = 27 if kernel_size == 3 else 1
+    kp = lib.stemseg_transposed_row_length(t, h, w, pad)
+    dev = dy.device
+    dy_t = _empty((planes, co, kp), torch.bfloat16, dev)
+    x_t = _empty((planes, ci, kp), torch.bfloat16, dev)
+    _check(lib.stemseg_transpose_pad(_lib.ptr(dy), 0, t, h, w, co, pad, _lib.ptr(dy_t), planes, _lib.stream_ptr()))
+    _check(lib.stemseg_transpose_pad(_lib.ptr(x_planes.tensor), 1, t, h, w, ci, pad, _lib.ptr(x_t), planes,
+                                     _lib.stream_ptr()))
+    ks = lib.stemseg_wgrad_k_splits(co, ci, kernel_size)
+    slices = _empty((ks, taps, co, ci), torch.float32, dev)
+    _check(lib.stemseg_conv3d_wgrad(_lib.ptr(dy_t), _lib.ptr(x_t), co, ci, t, h, w, kernel_size, planes, ks,
+                                    _lib.ptr(slices), _lib.stream_ptr()))
+    _check(lib.stemseg_wgrad_reduce(_lib.ptr(slices), ks, co, taps, ci, _lib.ptr(dst), dst.shape[1], cin_begin, 0,
+                                    _lib.stream_ptr()))
+
+
+def training_backward(head, saved, grad_out):
+    """-> (list of 4 feature gradients [1,C,T,h,w], {parameter name: gradient})."""
+    lib = _lib.load()
+    planes, tscale = saved["planes"], saved["tscale"]
+    spec = saved["out_spec"]
+    params = dict(head.named_parameters())
+    grads = {}
+    dgrad_w = _dgrad_weights(head)
+    dev = grad_out.device
+    g = grad_out.contiguous().to(torch.float32)
+
+    # ---- output heads ----------------------------------------------------------------------------------------------
+    m2 = saved["merges"][2]
+    z, y_low = m2["z"], m2["y_low"]
+    n, t, h, w, c3 = z.shape
+    dx = _empty((n, t, h, w, c3), torch.float32, dev)
+    d_wout = _empty((spec.n_out, c3), torch.float32, dev)
+    d_bout = _empty((spec.n_out,), torch.float32, dev)
+    ws_bytes = lib.stemseg_head_backward_workspace_bytes(c3)
+    ws = _empty((ws_bytes,), torch.uint8, dev)
+    _check(lib.stemseg_head_backward(_lib.ptr(z), _lib.ptr(y_low), n, t, h, w, c3, tscale[2], _lib.ptr(spec.weight),
+                                     _lib.ptr(spec.bias), _lib.ptr(spec.activation), spec.n_out, _lib.ptr(g),
+                                     _lib.ptr(dx), _lib.ptr(d_wout), _lib.ptr(d_bout), _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr()))
+    head._scatter_output_grads(d_wout, d_bout, grads)
+
+    # ---- merges (conv1x1(cat(up(x), f)) = up(W_a x) + W_b f), highest resolution first -----------------------------
+    branch_grad = [None] * 4
+    d_high = dx
+    for k in (2, 1, 0):
+        m = saved["merges"][k]
+        merge = D.MERGES[k]
+        wgrad_dst = torch.empty_like(params[merge + ".weight"])
+        wflat = wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 1)
+        nn_, th, hh, wh, ch = d_high.shape
+        d_low = _empty((nn_, th // tscale[k], hh // 2, wh // 2, ch), torch.float32, dev)
+        _check(lib.stemseg_upsample_transpose(_lib.ptr(d_high), nn_, th, hh, wh, ch, tscale[k], _lib.ptr(d_low),
+                                              _lib.stream_ptr()))
+        branch_grad[k + 1] = D.conv3d(_to_planes(d_high, planes), dgrad_w[(merge, "skip")])       # W_b^T dz
+        _wgrad(d_high, m["f_in"], 1, planes, wflat, m["x_in"].c)
+        d_xin = D.conv3d(_to_planes(d_low, planes), dgrad_w[(merge, "up")])                        # W_a^T d y_low
+        _wgrad(d_low, m["x_in"], 1, planes, wflat, 0)
+        grads[merge + ".weight"] = wgrad_dst
+        d_high = d_xin
+    branch_grad[0] = d_high
+
+    # ---- conv stages, last stage first -----------------------------------------------------------------------------
+    feat_grads = []
+    for b, (name, n_stages) in enumerate(D.BLOCKS):
+        d = branch_grad[b]
+        for j in reversed(range(n_stages)):
+            st = saved["blocks"][name][j]
+            y = st["y"]
+            nn_, t_, h_, w_, c_ = y.shape
+            dn = _empty((nn_, t_, h_, w_, c_), torch.float32, dev)
+            _check(lib.stemseg_pool_relu_backward(_lib.ptr(d), _lib.ptr(y), _lib.ptr(st["scale_shift"]), nn_, t_, h_, w_,
+                                                  c_, 1 if st["pool"] else 0, _lib.ptr(dn), _lib.stream_ptr()))
+            wname, bname = "%s.%d.weight" % (name, 4 * j), "%s.%d.bias" % (name, 4 * j)
+            if st["mean_rstd"] is not None:
+                groups = st["mean_rstd"].shape[1]
+                dgb = _empty((nn_, c_, 2), torch.float32, dev)
+                gterms = _empty((nn_, groups, 2), torch.float32, dev)
+                wsb = lib.stemseg_group_norm_backward_workspace_bytes(nn_, t_ * h_ * w_, c_)
+                wsg = _empty((wsb,), torch.uint8, dev)
+                _check(lib.stemseg_group_norm_backward(_lib.ptr(dn), _lib.ptr(y), _lib.ptr(st["mean_rstd"]),
+                                                       _lib.ptr(st["gamma"]), nn_, t_ * h_ * w_, c_, c_ // groups,
+                                                       _lib.ptr(dgb), _lib.ptr(gterms), _lib.ptr(wsg), wsb,
+                                                       _lib.stream_ptr()))
+                grads["%s.%d.weight" % (name, 4 * j + 1)] = dgb[0, :, 0].contiguous()
+                grads["%s.%d.bias" % (name, 4 * j + 1)] = dgb[0, :, 1].contiguous()
+            dy = dn                                               # GroupNorm backward ran in place
+            d_bias = _empty((c_,), torch.float32, dev)
+            wsb = lib.stemseg_channel_sum_workspace_bytes(t_ * h_ * w_, c_)
+            wsc = _empty((wsb,), torch.uint8, dev)
+            _check(lib.stemseg_channel_sum(_lib.ptr(dy), t_ * h_ * w_, c_, _lib.ptr(d_bias), _lib.ptr(wsc), wsb,
+                                           _lib.stream_ptr()))
+            grads[bname] = d_bias
+            wgrad_dst = torch.empty_like(params[wname])
+            _wgrad(dy, st["a_in"], 3, planes, wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 27), 0)
+            grads[wname] = wgrad_dst
+            d = D.conv3d(_to_planes(dy, planes), dgrad_w[wname])     # dgrad: conv with flipped / transposed weights
+        feat_grads.append(d.permute(0, 4, 1, 2, 3))                  # NDHWC -> NCTHW view
+    return feat_grads, grads
+
+
+class HeadFunction(torch.autograd.Function):
+    """autograd node of one head: inputs = 4 feature maps + all parameters (so DDP / optimisers see the gradients)."""
+
+    @staticmethod
+    def forward(ctx, head, n_feats, *tensors):
+        feats = list(tensors[:n_feats])
+        with torch.no_grad():
+            out, saved = training_forward(head, [f.detach() for f in feats])
+        ctx.head, ctx.saved_state = head, saved
+        ctx.param_names = [n for n, _ in head.named_parameters()]
+        ctx.feat_needs = [f.requires_grad for f in feats]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        with torch.no_grad():
+            feat_grads, pgrads = training_backward(ctx.head, ctx.saved_state, grad_out)
+        ctx.saved_state = None
+        outs = [None, None]
+        outs += [fg if need else None for fg, need in zip(feat_grads, ctx.feat_needs)]
+        for name in ctx.param_names:
+            gr = pgrads.get(name)
+            outs.append(None if gr is None else gr)
+        return tuple(outs)
+
+
+def run_head_with_grad(head, feats_32_16_8_4):
+    params = [p for _, p in head.named_parameters()]
+    return HeadFunction.apply(head, len(feats_32_16_8_4), *feats_32_16_8_4, *params)

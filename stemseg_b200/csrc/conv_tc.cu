@@ -43,6 +43,12 @@ struct ConvTcParams {
     int num_tiles;             // n * tiles_t * tiles_h * tiles_w * n_tiles_n * k_slices
     float* out;                // [k_slices][n][t][h][w][cout] fp32 (partial sums when k_slices > 1)
     const float* bias;         // [cout] or nullptr
+    // ---- wgrad mode (backward_ops.cu): plain K-major GEMM out[m][n] = sum_k A[m][k] B[n][k + b_k_offset[slice]] over the
+    // zero-padded transposed planes; slice = filter tap, K range additionally split over k_splits CTAs ---------------
+    int wgrad_mode;
+    int b_k_offset[27];
+    int k_splits;              // >= 1
+    int k_chunks_total;        // K chunks of the whole reduction (cin / BLOCK_K in normal mode)
     int tiles_per_cta;         // 0: persistent (tile = blockIdx.x + k*gridDim.x); >0: CTA b owns tiles [b*tpc, (b+1)*tpc)
                                // so that a long layer is a stream of short-lived CTAs and higher-priority kernels of
                                // other graph branches get SMs while it runs
@@ -204,12 +210,14 @@ constexpr int stage_bytes() {
 }
 
 struct TileCoord {
-    int n, t0, h0, w0, n_tile, slice;
+    int n, t0, h0, w0, n_tile, slice, ksplit;
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile) {
     TileCoord c;
     c.slice = tile % p.k_slices;
     tile /= p.k_slices;
+    c.ksplit = tile % p.k_splits;
+    tile /= p.k_splits;
     c.n_tile = tile % p.n_tiles_n;
     int m = tile / p.n_tiles_n;
     c.w0 = (m % p.tiles_w) * p.tw;
@@ -252,7 +260,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_chunks = p.cin / BLOCK_K;
-    const int num_k_blocks = p.taps_per_slice * k_chunks;
+    const int chunks_per_split = (k_chunks + p.k_splits - 1) / p.k_splits;      // only k_splits > 1 in wgrad mode
+    auto k_blocks_of = [&](const TileCoord& tc) -> int {
+        if (p.k_splits == 1) return p.taps_per_slice * k_chunks;
+        const int begin = tc.ksplit * chunks_per_split;
+        const int end = begin + chunks_per_split < k_chunks ? begin + chunks_per_split : k_chunks;
+        return end > begin ? end - begin : 0;
+    };
     int tile_first = blockIdx.x, tile_last = p.num_tiles, tile_step = gridDim.x;
     if (p.tiles_per_cta > 0) {
         tile_first = blockIdx.x * p.tiles_per_cta;
@@ -295,8 +309,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
             uint32_t phase = 0;
             for (int tile = tile_first; tile < tile_last; tile += tile_step) {
                 const TileCoord tc = decode_tile(p, tile);
+                const int num_k_blocks = k_blocks_of(tc);
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    const int tap = tc.slice * p.taps_per_slice + kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
+                    int tap = tc.slice * p.taps_per_slice + kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
+                    if (p.wgrad_mode) {
+                        tap = 0;
+                        c0 = (tc.ksplit * chunks_per_split + kb) * BLOCK_K;
+                    }
                     int dt = 0, dh = 0, dw = 0;
                     if (p.ntaps == 27) {
                         dt = tap / 9 - 1;
@@ -310,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                     if (PLANES == 2)
                         tma_load_5d(&a_map1, full_bar + stage, st + A_BYTES, c0, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n);
                     uint8_t* sb = st + PLANES * A_BYTES;
-                    const int kcoord = tap * p.cin + c0;
+                    const int kcoord = p.wgrad_mode ? c0 + p.b_k_offset[tc.slice] : tap * p.cin + c0;
                     tma_load_2d(&b_map0, full_bar + stage, sb, kcoord, tc.n_tile * BLOCK_N);
                     if (PLANES == 2) tma_load_2d(&b_map1, full_bar + stage, sb + B_BYTES, kcoord, tc.n_tile * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -328,6 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
             mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);       // epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+            const int num_k_blocks = k_blocks_of(decode_tile(p, tile));
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 mbar_wait(full_bar + stage, phase);                // TMA bytes have landed
                 tcgen05_fence_after();
@@ -378,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(acc * BLOCK_N);
             if (p.epi_mode == 0) {
-                float* out_row = p.out + tc.slice * p.slice_stride +
+                float* out_row = p.out + (static_cast<size_t>(tc.ksplit) * p.k_slices + tc.slice) * p.slice_stride +
                                  ((((static_cast<size_t>(tc.n) * p.t + t) * p.h + h) * p.w + w) * p.cout +
                                   static_cast<size_t>(tc.n_tile) * BLOCK_N);
                 const float* bias = (p.bias && tc.slice == 0) ? p.bias + tc.n_tile * BLOCK_N : nullptr;
@@ -420,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                 if (stats) {
                     asm volatile("bar.sync 1, %0;" ::"n"(kNumEpilogueThreads) : "memory");
                     const int et = threadIdx.x - (kNumThreads - kNumEpilogueThreads);
-                    const int m_in_sample = (tile / (p.k_slices * p.n_tiles_n)) % p.tiles_per_sample;
+                    const int m_in_sample = (tile / (p.k_slices * p.k_splits * p.n_tiles_n)) % p.tiles_per_sample;
                     for (int col = et; col < BLOCK_N; col += kNumEpilogueThreads) {
                         float a = 0.f, b = 0.f;
 #pragma unroll
@@ -699,6 +719,10 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     p.out = out;
     p.bias = bias;
     p.num_stages = 0;
+    p.wgrad_mode = 0;
+    p.k_splits = 1;
+    p.k_chunks_total = 0;
+    for (int i = 0; i < 27; ++i) p.b_k_offset[i] = 0;
     p.tiles_per_cta = s->tiles_per_cta > 0 ? s->tiles_per_cta : 0;
     p.tiles_per_sample = p.tiles_t * p.tiles_h * p.tiles_w;
     p.stat_partial = stat_partial;
@@ -773,4 +797,82 @@ extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const voi
     head.t_abs = time_scale;
     head.head_out = out;
     return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, nullptr, s, max_ctas, stream_, &head);
+}
+
+extern "C" int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t kernel_size) {
+    const int taps = kernel_size == 3 ? 27 : 1;
+    const long long tiles = 1ll * ((cout + kBlockM - 1) / kBlockM) * (cin / block_n_for(cin)) * taps;
+    long long k = (3ll * device_sm_count() + tiles - 1) / tiles;
+    if (k < 1) k = 1;
+    if (k > 32) k = 32;
+    return static_cast<int32_t>(k);
+}
+
+// dW partial sums for a stride-1 / pad-(k-1)/2 convolution from the zero-padded transposed planes:
+//   slices[ks][tap][co][ci] = sum_{p in K range ks} dyT[co][p] * xT[ci][p + delta(tap)]
+extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_planes, int32_t cout, int32_t cin,
+                                        int32_t t, int32_t h, int32_t w, int32_t kernel_size, int32_t planes,
+                                        int32_t k_splits, float* slices, void* stream_) {
+    SS_REQUIRE(dyT_planes && xT_planes && slices, "conv3d_wgrad: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "conv3d_wgrad: planes must be 1 or 2");
+    SS_REQUIRE(kernel_size == 3 || kernel_size == 1, "conv3d_wgrad: kernel_size must be 1 or 3");
+    SS_REQUIRE(cout >= 1 && cin >= 32 && cin % 32 == 0, "conv3d_wgrad: cin must be a multiple of 32 (got %d)", cin);
+    SS_REQUIRE(k_splits >= 1 && k_splits <= 64, "conv3d_wgrad: k_splits out of range");
+    int rc = require_sm100();
+    if (rc != STEMSEG_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int pad = kernel_size == 3 ? 1 : 0;
+    const long long k_true = 1ll * (t + 2 * pad) * (h + 2 * pad) * (w + 2 * pad);
+    const long long k_pad = (k_true + 63) / 64 * 64;
+    SS_REQUIRE(k_pad < 0x7FFFFFFFll, "conv3d_wgrad: volume too large");
+
+    ConvTcParams p;
+    p.n = 1; p.t = 1; p.h = 1; p.w = cout;                 // GEMM rows = output channels of the convolution
+    p.cin = static_cast<int>(k_pad);                       // GEMM K = padded voxels
+    p.cout = cin;                                          // GEMM N = input channels of the convolution
+    p.ntaps = 1;
+    choose_box(1, 1, cout, &p.tt, &p.th, &p.tw);
+    p.tiles_t = 1; p.tiles_h = 1;
+    p.tiles_w = (cout + p.tw - 1) / p.tw;
+    const int block_n = block_n_for(cin);
+    p.n_tiles_n = cin / block_n;
+    p.k_slices = kernel_size == 3 ? 27 : 1;
+    p.taps_per_slice = 1;
+    p.slice_stride = static_cast<size_t>(cout) * cin;
+    p.k_splits = k_splits;
+    p.wgrad_mode = 1;
+    const int hp = h + 2 * pad, wp = w + 2 * pad;
+    for (int tap = 0; tap < 27; ++tap) {
+        const int dt = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+        p.b_k_offset[tap] = kernel_size == 3 ? (dt * hp + dh) * wp + dw : 0;
+    }
+    const long long tiles = 1ll * p.tiles_w * p.n_tiles_n * p.k_slices * p.k_splits;
+    p.num_tiles = static_cast<int>(tiles);
+    p.out = slices;
+    p.bias = nullptr;
+    p.num_stages = 0;
+    p.tiles_per_cta = 0;
+    p.tiles_per_sample = p.tiles_w;
+    p.stat_partial = nullptr;
+    p.epi_mode = 0;
+    p.head_j = 0;
+    p.k_chunks_total = 0;
+
+    int block_k = 64;
+    if (planes == 2 && block_n == 256) block_k = 32;
+    const size_t a_plane_bytes = static_cast<size_t>(cout) * k_pad * 2;
+    const size_t b_plane_bytes = static_cast<size_t>(cin) * k_pad * 2;
+    CUtensorMap maps[4];
+    const uint8_t* a = static_cast<const uint8_t*>(dyT_planes);
+    const uint8_t* b = static_cast<const uint8_t*>(xT_planes);
+    for (int pl = 0; pl < 2; ++pl) {
+        const int src = pl < planes ? pl : 0;
+        rc = encode_act_map(&maps[pl], a + src * a_plane_bytes, p, block_k);
+        if (rc != STEMSEG_OK) return rc;
+        rc = encode_weight_map(&maps[2 + pl], b + src * b_plane_bytes, k_pad, cin, block_k, block_n);
+        if (rc != STEMSEG_OK) return rc;
+    }
+    if (planes == 2)
+        return block_k == 64 ? launch_by_n<64, 2>(block_n, maps, p, 0, stream) : launch_by_n<32, 2>(block_n, maps, p, 0, stream);
+    return block_k == 64 ? launch_by_n<64, 1>(block_n, maps, p, 0, stream) : launch_by_n<32, 1>(block_n, maps, p, 0, stream);
 }

@@ -86,6 +86,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int 
     }
 }
 
+// dgrad weights: conv(dy, W') with W'[ci][taps-1-tap][co] = W[co][ci][tap] (flipped taps, swapped channels)
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ src, int cout, int cin_total, int cin_begin,
+                                         int cin_count, int taps, __nv_bfloat16* __restrict__ dst, size_t plane_elems,
+                                         int planes) {
+    const long long total = 1ll * cin_count * taps * cout;
+    for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+        const int co = static_cast<int>(i % cout);
+        const int tapf = static_cast<int>((i / cout) % taps);
+        const int ci = static_cast<int>(i / (1ll * cout * taps));
+        const float x = src[(static_cast<size_t>(co) * cin_total + cin_begin + ci) * taps + (taps - 1 - tapf)];
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        dst[i] = h;
+        if (planes == 2) dst[plane_elems + i] = l;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K2a: per-channel partial sums of an NDHWC fp32 tensor; K2b: finalize per (sample, group) mean / rstd.
 // Replaces the statistics pass of nn.GroupNorm(32, C) (model_builder.py:34; embedding_decoder.py:22,...).
@@ -160,7 +177,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(float* __restrict__ x, 
 __global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restrict__ partial, size_t sample_stride,
                                                           int chunks, int c, int cpg, long long spatial, float eps,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ scale_shift /*[n][c][2]*/) {
+                                                          float* __restrict__ scale_shift /*[n][c][2]*/,
+                                                          float* __restrict__ mean_rstd /*[n][groups][2] or null*/) {
     const int g = blockIdx.x, n = blockIdx.y;
     double s = 0.0, ss = 0.0;
     // the cpg channels of a group are contiguous in the [n][c][chunks][2] layout: one coalesced stream
@@ -193,6 +211,11 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restric
         const float sc = rstd * gamma[ch];
         o[0] = sc;
         o[1] = beta[ch] - m * sc;
+        if (mean_rstd != nullptr && threadIdx.x == 0) {
+            float* mr = mean_rstd + (static_cast<size_t>(n) * (c / cpg) + g) * 2;
+            mr[0] = m;
+            mr[1] = rstd;
+        }
     }
 }
 
@@ -585,6 +608,21 @@ static int stats_chunk_voxels(int64_t spatial) {
     return static_cast<int>(chunk);
 }
 
+extern "C" int32_t stemseg_pack_conv_weight_dgrad(const float* src, int32_t cout, int32_t cin_total, int32_t cin_begin,
+                                                  int32_t cin_count, int32_t taps, void* dst_planes, int32_t planes,
+                                                  void* stream_) {
+    SS_REQUIRE(src && dst_planes, "pack_conv_weight_dgrad: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight_dgrad: planes must be 1 or 2");
+    SS_REQUIRE(cout >= 1 && cin_count >= 1 && cin_begin >= 0 && cin_begin + cin_count <= cin_total && taps >= 1,
+               "pack_conv_weight_dgrad: bad shape");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t plane_elems = static_cast<size_t>(cin_count) * taps * cout;
+    pack_weight_dgrad_kernel<<<grid_for(static_cast<long long>(plane_elems), 256), 256, 0, stream>>>(
+        src, cout, cin_total, cin_begin, cin_count, taps, static_cast<__nv_bfloat16*>(dst_planes), plane_elems, planes);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
 extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial, int32_t c) {
     const long long chunks = (spatial + 7) / 8;          // upper bound over every chunk size that may be chosen
     return align_up(static_cast<size_t>(n) * chunks * c * 2 * sizeof(float), 256);
@@ -593,7 +631,7 @@ extern "C" size_t stemseg_group_norm_workspace_bytes(int32_t n, int64_t spatial,
 extern "C" int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_t slices, int32_t n,
                                             int64_t spatial, int32_t c, int32_t channels_per_group, float eps,
                                             const float* gamma, const float* beta, float* scale_shift,
-                                            void* workspace, size_t workspace_bytes, void* stream_) {
+                                            float* mean_rstd, void* workspace, size_t workspace_bytes, void* stream_) {
     SS_REQUIRE(x && scale_shift && gamma && beta && workspace, "group_norm_stats: null pointer");
     SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_stats: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && channels_per_group <= 512 && c % channels_per_group == 0,
@@ -619,7 +657,7 @@ extern "C" int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_
                                                                   chunk_voxels, static_cast<float*>(workspace), chunks);
     gn_finalize_kernel<<<dim3(c / channels_per_group, n), 512, 0, stream>>>(
         static_cast<const float*>(workspace), static_cast<size_t>(c) * chunks * 2, chunks, c, channels_per_group,
-        spatial, eps, gamma, beta, scale_shift);
+        spatial, eps, gamma, beta, scale_shift, mean_rstd);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
@@ -627,7 +665,7 @@ extern "C" int32_t stemseg_group_norm_stats(float* x, int32_t row_stride, int32_
 extern "C" int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample_stride, int32_t chunks,
                                                int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
                                                float eps, const float* gamma, const float* beta, float* scale_shift,
-                                               void* stream_) {
+                                               float* mean_rstd, void* stream_) {
     SS_REQUIRE(partial && gamma && beta && scale_shift, "group_norm_finalize: null pointer");
     SS_REQUIRE(n >= 1 && spatial >= 1 && chunks >= 1 && c >= 1, "group_norm_finalize: bad shape");
     SS_REQUIRE(channels_per_group >= 1 && channels_per_group <= 512 && c % channels_per_group == 0,
@@ -636,7 +674,7 @@ extern "C" int32_t stemseg_group_norm_finalize(const float* partial, int64_t par
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     gn_finalize_kernel<<<dim3(c / channels_per_group, n), 512, 0, stream>>>(
         partial, static_cast<size_t>(partial_sample_stride), chunks, c, channels_per_group, spatial, eps, gamma, beta,
-        scale_shift);
+        scale_shift, mean_rstd);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

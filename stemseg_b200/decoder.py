@@ -158,7 +158,8 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked
     return out
 
 
-def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None, stat=None):
+def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None, stat=None,
+                         saved=None):
     """fp32 NDHWC conv output ([split_k,] n,t,h,w,c_total) -> relu(GN(y)) [-> avgpool] as Planes.
 
     gamma None = no normalisation.  channel_slice=(c0, c) normalises channels [c0, c0+c) of a wider (multi-head)
@@ -171,6 +172,9 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
     x_ptr = _lib.c_void_p(y.data_ptr() + 4 * c0)
     with torch.cuda.device(dev):
         scale_shift = None
+        mean_rstd_out = None
+        if gamma is not None and saved is not None:          # training: keep the group statistics for the backward
+            mean_rstd_out = torch.empty((n, num_groups, 2), dtype=torch.float32, device=dev)
         if gamma is not None:
             if c % num_groups != 0:
                 raise ValueError("channels %d not divisible by %d groups" % (c, num_groups))
@@ -180,20 +184,24 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
                 part_ptr = _lib.c_void_p(stat.data_ptr() + 4 * c0 * chunks * 2)
                 _check(lib.stemseg_group_norm_finalize(part_ptr, c_total * chunks * 2, chunks, n, t * h * w, c,
                                                        c // num_groups, float(eps), _lib.ptr(gamma), _lib.ptr(beta),
-                                                       _lib.ptr(scale_shift), _lib.stream_ptr()))
+                                                       _lib.ptr(scale_shift), _lib.ptr(mean_rstd_out),
+                                                       _lib.stream_ptr()))
                 KEEP.append(scale_shift)
             else:
                 ws_bytes = lib.stemseg_group_norm_workspace_bytes(n, t * h * w, c)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 _check(lib.stemseg_group_norm_stats(x_ptr, c_total, slices, n, t * h * w, c, c // num_groups,
                                                     float(eps), _lib.ptr(gamma), _lib.ptr(beta),
-                                                    _lib.ptr(scale_shift), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+                                                    _lib.ptr(scale_shift), _lib.ptr(mean_rstd_out), _lib.ptr(ws),
+                                                    ws_bytes, _lib.stream_ptr()))
                 KEEP.extend((ws, scale_shift))
             slices = 1                               # the statistics pass summed the split-K slices into slice 0
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
         _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c,
                                           1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
+    if saved is not None:
+        saved["scale_shift"], saved["mean_rstd"] = scale_shift, mean_rstd_out
     return Planes(dst, n, t_out, h, w, c)
 
 

@@ -118,11 +118,17 @@ class _SqueezeExpandTrunk(nn.Module):
                                        use_graph=self.use_cuda_graph)
         return self._head_set
 
+    def _scatter_output_grads(self, d_weight, d_bias, grads):
+        """Rows of the fused output-conv gradient [J, c3] / [J] -> this head's parameter names."""
+        raise NotImplementedError
+
     def _run(self, feats_32_16_8_4, trace=None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
-                any(f.requires_grad for f in feats_32_16_8_4):
-            raise NotImplementedError("the CUDA decoder is inference-only in this round (backward kernels are a "
-                                      "'next' row, SURVEY.md §8f); call it under torch.no_grad()")
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                                  any(f.requires_grad for f in feats_32_16_8_4))
+        if needs_grad:
+            # training: eager CUDA forward that keeps its intermediates + hand-written backward (autograd.py)
+            from stemseg_b200.autograd import run_head_with_grad
+            return run_head_with_grad(self, feats_32_16_8_4)
         with torch.no_grad():
             head_set = self._get_head_set()
             return head_set.run(feats_32_16_8_4, trace=None if trace is None else (0, trace))[0]
@@ -174,6 +180,14 @@ class EmbeddingHead(_SqueezeExpandTrunk):
         return D.OutputSpec(torch.cat([w.detach() for w in ws], 0), torch.cat([b.detach() for b in bias], 0), act,
                             coord, float(self.time_scale))
 
+    def _scatter_output_grads(self, d_weight, d_bias, grads):
+        e_out, v = self.conv_embedding.weight.shape[0], self.variance_channels
+        grads["conv_embedding.weight"] = d_weight[:e_out].reshape(self.conv_embedding.weight.shape)
+        grads["conv_variance.weight"] = d_weight[e_out:e_out + v].reshape(self.conv_variance.weight.shape)
+        grads["conv_variance.bias"] = d_bias[e_out:e_out + v].contiguous()
+        if self.conv_seediness is not None:
+            grads["conv_seediness.weight"] = d_weight[e_out + v:e_out + v + 1].reshape(self.conv_seediness.weight.shape)
+
     def forward(self, x, trace=None):
         """x: list of 4 feature maps [N, C, T, H, W] in increasing spatial size (strides 32, 16, 8, 4)."""
         assert len(x) == 4, "Expected 4 feature maps, got {}".format(len(x))
@@ -193,6 +207,9 @@ class SeedinessHead(_SqueezeExpandTrunk):
 
     def _output_spec(self, state):
         return D.OutputSpec(self.conv_out.weight.reshape(1, -1), None, [D.ACT_SIGMOID], [D.COORD_NONE])
+
+    def _scatter_output_grads(self, d_weight, d_bias, grads):
+        grads["conv_out.weight"] = d_weight.reshape(self.conv_out.weight.shape)
 
     def forward(self, x, trace=None):
         assert len(x) == 4
@@ -218,6 +235,9 @@ class SemsegHead(_SqueezeExpandTrunk):
     def _output_spec(self, state):
         j = self.conv_out.weight.shape[0]
         return D.OutputSpec(self.conv_out.weight.reshape(j, -1), None, [D.ACT_IDENTITY] * j, [D.COORD_NONE] * j)
+
+    def _scatter_output_grads(self, d_weight, d_bias, grads):
+        grads["conv_out.weight"] = d_weight.reshape(self.conv_out.weight.shape)
 
     def forward(self, x, trace=None):
         assert len(x) == 4, "Expected 4 feature maps, got {}".format(len(x))

@@ -1,0 +1,135 @@
+"""Training backward of the B200 heads vs torch autograd over the CPU oracle.
+
+The oracle (oracle/decoder_oracle.py) is evaluated in float64 on the CPU with autograd; the CUDA path must reproduce
+d loss / d feature and d loss / d parameter for loss = <out, R> (R seeded) norm-wise within GRAD_TOL.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_oracle as do
+import decoder_cases as dc
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-3          # norm-wise relative error of every gradient tensor (fp32 mode: bf16x2 split operands)
+FWD_TOL = 1e-4
+
+BACKWARD_CASES = ["semseg_4_t4", "emb_xyff_t8", "emb_xytff_t16", "emb_ff_notanh_t4", "emb_xyff_t2", "seediness_t8",
+                  "emb_fullwidth_t8"]
+
+
+def _build_head(case, device, norm=True):
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    norm_type = (lambda c: nn.GroupNorm(32, c)) if norm else nn.Identity
+    if case["kind"] == "embedding":
+        head = heads.EmbeddingHead(case["in_channels"], case["inter"], case["embedding_size"], case["tanh"],
+                                   case["seediness_output"], case["dim_mode"], NormType=norm_type,
+                                   num_frames=case["num_frames"])
+    elif case["kind"] == "seediness":
+        head = heads.SeedinessHead(case["in_channels"], case["inter"], NormType=norm_type,
+                                   num_frames=case["num_frames"])
+    else:
+        head = heads.SemsegHead(case["in_channels"], case["num_out"], case["inter"], (4, 8, 16, 32),
+                                NormType=norm_type, num_frames=case["num_frames"])
+    return head.to(device)
+
+
+def _oracle_forward(case, sd, feats, gn_groups=32):
+    if case["kind"] == "embedding":
+        return do.embedding_head(sd, feats, case["num_frames"], case["embedding_size"], case["dim_mode"], case["tanh"],
+                                 case["seediness_output"], gn_groups=gn_groups)
+    if case["kind"] == "seediness":
+        return do.seediness_head(sd, feats, case["num_frames"], gn_groups=gn_groups)
+    return do.semseg_head(sd, feats, case["num_frames"], gn_groups=gn_groups)
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / max(b.norm().item(), 1e-30))
+
+
+def _check_case(case, sd, feats, device, norm=True):
+    # reference gradients: float64 autograd through the oracle
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and v.dim() > 0}
+    sd_ref = dict(sd)
+    sd_ref.update(sd64)
+    f64 = [f.double().clone().requires_grad_(True) for f in feats]
+    ref = _oracle_forward(case, sd_ref, f64, gn_groups=32 if norm else 0)
+    gen = torch.Generator().manual_seed(4242)
+    r = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    (ref * r).sum().backward()
+
+    head = _build_head(case, device, norm)
+    head.load_state_dict(sd, strict=True)
+    head.train()
+    fdev = [f.to(device).requires_grad_(True) for f in feats]
+    out = head(fdev)
+    assert out.requires_grad
+    assert _rel(out.detach(), ref.detach()) <= FWD_TOL
+    (out * r.to(device=device, dtype=torch.float32)).sum().backward()
+    torch.cuda.synchronize()
+
+    errors = {}
+    for i, (fd, fr) in enumerate(zip(fdev, f64)):
+        errors["feature[%d]" % i] = _rel(fd.grad, fr.grad)
+    for name, p in head.named_parameters():
+        assert p.grad is not None, name
+        assert p.grad.shape == p.shape, name
+        errors[name] = _rel(p.grad, sd64[name].grad)
+    bad = {k: v for k, v in errors.items() if not (v <= GRAD_TOL)}
+    print("max gradient error %.3g" % max(errors.values()))
+    assert not bad, "gradient mismatch: %s (all: %s)" % (bad, errors)
+
+
+@pytest.mark.parametrize("name", BACKWARD_CASES)
+def test_head_gradients_match_autograd(name, cuda_device):
+    sd, feats, case = dc.build_case(name)
+    if case["n"] != 1:
+        pytest.skip("backward handles one sub-clip per call")
+    _check_case(case, sd, feats, cuda_device)
+
+
+def test_head_gradients_without_normalisation(cuda_device):
+    case = dict(kind="seediness", in_channels=32, inter=[32, 32, 32, 32], num_frames=8, n=1, h4=24, w4=24)
+    shapes = do.head_parameter_shapes("seediness", 32, [32, 32, 32, 32], gn=False)
+    sd = do.seeded_state_dict(shapes, 77)
+    feats = do.seeded_features(78, 1, 32, 8, 24, 24)
+    _check_case(case, sd, feats, cuda_device, norm=False)
+
+
+def test_only_parameters_need_grad(cuda_device):
+    """Frozen backbone (features without grad) still trains the head; frozen head still back-propagates to features."""
+    sd, feats, case = dc.build_case("semseg_4_t4")
+    head = _build_head(case, cuda_device)
+    head.load_state_dict(sd, strict=True)
+    out = head([f.to(cuda_device) for f in feats])
+    out.sum().backward()
+    assert all(p.grad is not None for p in head.parameters())
+    g_ref = {n: p.grad.clone() for n, p in head.named_parameters()}
+    head.zero_grad()
+    for p in head.parameters():
+        p.requires_grad_(False)
+    fdev = [f.to(cuda_device).requires_grad_(True) for f in feats]
+    head(fdev).sum().backward()
+    assert all(f.grad is not None and f.grad.shape == f.shape for f in fdev)
+    assert all(p.grad is None for p in head.parameters())
+    # an optimiser step invalidates the packed weights (forward after the step sees the new parameters)
+    for p in head.parameters():
+        p.requires_grad_(True)
+    opt = torch.optim.SGD(head.parameters(), lr=1e-2)
+    before = head([f.to(cuda_device) for f in feats]).detach().clone()
+    for n, p in head.named_parameters():
+        p.grad = g_ref[n]
+    opt.step()
+    after = head([f.to(cuda_device) for f in feats]).detach()
+    assert (before - after).abs().max().item() > 0
+
+
+def test_batched_training_fails_loudly(cuda_device):
+    sd, feats, case = dc.build_case("emb_xyt_t8_batch2")
+    head = _build_head(case, cuda_device)
+    head.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        head([f.to(cuda_device).requires_grad_(True) for f in feats])
