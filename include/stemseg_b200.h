@@ -313,13 +313,19 @@ int32_t stemseg_channel_sum(const float* x, int64_t rows, int32_t c, float* out,
                             void* stream);
 /* fp32 -> bf16 planes without activation (gradients entering a dgrad GEMM) */
 int32_t stemseg_to_planes(const float* x, int64_t elems, void* dst_planes, int32_t planes, void* stream);
-/* [t*h*w][c] (fp32, or bf16 planes when src_is_planes) -> zero-padded transposed bf16 planes [P][c][row_length] with
- * row_length = stemseg_transposed_row_length(t, h, w, pad) and element (t,y,x) at ((t+pad)(h+2pad)+(y+pad))(w+2pad)+x+pad */
+/* [t*h*w][c] (fp32, or bf16 planes when src_is_planes) -> zero-padded transposed bf16 planes [P][shifts][c][row_length]
+ * with row_length = stemseg_transposed_row_length(t, h, w, pad) and element (t,y,x) at
+ * ((t+pad)(h+2pad)+(y+pad))*pitch + x+pad, pitch = w (pad 0) or round_up(w+2, 8) (pad 1).  shifts = 3 (pad 1 only)
+ * writes three copies shifted by dw = -1, 0, +1 along the row (copy[q] = x[q+dw]): a TMA load needs a 16-byte
+ * aligned start coordinate in the contiguous dimension, so the dw part of a filter-tap offset is taken from the copy
+ * and only the (dt, dh) part (a multiple of the pitch) from the coordinate. */
 int64_t stemseg_transposed_row_length(int32_t t, int32_t h, int32_t w, int32_t pad);
 int32_t stemseg_transpose_pad(const void* src, int32_t src_is_planes, int32_t t, int32_t h, int32_t w, int32_t c,
-                              int32_t pad, void* dst_planes, int32_t planes, void* stream);
+                              int32_t pad, int32_t shifts, void* dst_planes, int32_t planes, void* stream);
 /* slices [k_splits][taps][cout][cin] fp32 partial weight gradients; see the section comment */
-int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t kernel_size);
+int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t t, int32_t h, int32_t w, int32_t kernel_size,
+                               int32_t planes);
+/* dyT_planes: transpose_pad with shifts 1; xT_planes: shifts 3 when kernel_size is 3, else 1 */
 int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_planes, int32_t cout, int32_t cin, int32_t t,
                              int32_t h, int32_t w, int32_t kernel_size, int32_t planes, int32_t k_splits, float* slices,
                              void* stream);

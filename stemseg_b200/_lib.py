@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -86,9 +86,9 @@ PROTOTYPES = {
     "stemseg_channel_sum": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_to_planes": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "stemseg_transposed_row_length": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
-    "stemseg_transpose_pad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
-                                        c_int32, c_void_p]),
-    "stemseg_wgrad_k_splits": (c_int32, [c_int32, c_int32, c_int32]),
+    "stemseg_transpose_pad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_int32, c_void_p]),
+    "stemseg_wgrad_k_splits": (c_int32, [c_int32] * 7),
     "stemseg_conv3d_wgrad": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_int32, c_void_p, c_void_p]),
     "stemseg_wgrad_reduce": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,

@@ -122,12 +122,13 @@ def _wgrad(dy, x_planes, kernel_size, planes, dst, cin_begin):
     taps = 27 if kernel_size == 3 else 1
     kp = lib.stemseg_transposed_row_length(t, h, w, pad)
     dev = dy.device
+    shifts = 3 if kernel_size == 3 else 1      # pre-shifted copies of x: TMA start coordinates must be 16-byte aligned
     dy_t = _empty((planes, co, kp), torch.bfloat16, dev)
-    x_t = _empty((planes, ci, kp), torch.bfloat16, dev)
-    _check(lib.stemseg_transpose_pad(_lib.ptr(dy), 0, t, h, w, co, pad, _lib.ptr(dy_t), planes, _lib.stream_ptr()))
-    _check(lib.stemseg_transpose_pad(_lib.ptr(x_planes.tensor), 1, t, h, w, ci, pad, _lib.ptr(x_t), planes,
+    x_t = _empty((planes, shifts, ci, kp), torch.bfloat16, dev)
+    _check(lib.stemseg_transpose_pad(_lib.ptr(dy), 0, t, h, w, co, pad, 1, _lib.ptr(dy_t), planes, _lib.stream_ptr()))
+    _check(lib.stemseg_transpose_pad(_lib.ptr(x_planes.tensor), 1, t, h, w, ci, pad, shifts, _lib.ptr(x_t), planes,
                                      _lib.stream_ptr()))
-    ks = lib.stemseg_wgrad_k_splits(co, ci, kernel_size)
+    ks = lib.stemseg_wgrad_k_splits(co, ci, t, h, w, kernel_size, planes)
     slices = _empty((ks, taps, co, ci), torch.float32, dev)
     _check(lib.stemseg_conv3d_wgrad(_lib.ptr(dy_t), _lib.ptr(x_t), co, ci, t, h, w, kernel_size, planes, ks,
                                     _lib.ptr(slices), _lib.stream_ptr()))

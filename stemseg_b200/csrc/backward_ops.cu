@@ -464,11 +464,16 @@ __global__ void __launch_bounds__(256) to_planes_kernel(const float* __restrict_
 }
 
 constexpr int kTrC = 32, kTrV = 32;
+// pitch of one padded row of the transposed planes: a multiple of 8 bf16 so that every (dt, dh) tap offset is a
+// multiple of 16 bytes -- a tiled TMA load faults ("illegal instruction") when the start coordinate of the contiguous
+// dimension is not 16-byte aligned (measured on B200, scripts/tma_probe.cu)
+__host__ __device__ __forceinline__ int padded_row_pitch(int w, int pad) { return pad ? (w + 2 * pad + 7) / 8 * 8 : w; }
 // SRC_BF16 = false: src fp32 [n=1][t][h][w][c];  true: src bf16 planes [P][t*h*w][c]
 template <bool SRC_BF16>
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const void* __restrict__ src, int t, int h, int w, int c,
-                                                            int pad, long long k_pad, size_t src_plane_elems,
-                                                            __nv_bfloat16* __restrict__ dst, int planes) {
+                                                            int pad, int shifts, long long k_pad,
+                                                            size_t src_plane_elems, __nv_bfloat16* __restrict__ dst,
+                                                            int planes) {
     __shared__ float tile_hi[kTrV][kTrC + 1];
     __shared__ float tile_lo[kTrV][kTrC + 1];
     const long long spatial = 1ll * t * h * w;
@@ -497,7 +502,8 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const void* __restri
         tile_lo[ty + 8 * i][tx] = lo;
     }
     __syncthreads();
-    const int hp = h + 2 * pad, wp = w + 2 * pad;
+    const int hp = h + 2 * pad, wp = padded_row_pitch(w, pad);
+    const size_t plane_stride = static_cast<size_t>(shifts) * c * k_pad;
 #pragma unroll
     for (int i = 0; i < kTrC / 8; ++i) {
         const int cc = c0 + ty + 8 * i;
@@ -507,10 +513,15 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const void* __restri
             const int yh = static_cast<int>((v / w) % h);
             const int tt = static_cast<int>(v / (1ll * w * h));
             const long long p = (1ll * (tt + pad) * hp + (yh + pad)) * wp + (xw + pad);
-            dst[static_cast<size_t>(cc) * k_pad + p] = __float2bfloat16_rn(tile_hi[tx][ty + 8 * i]);
-            if (planes == 2)
-                dst[static_cast<size_t>(c) * k_pad + static_cast<size_t>(cc) * k_pad + p] =
-                    __float2bfloat16_rn(tile_lo[tx][ty + 8 * i]);
+            const __nv_bfloat16 bh = __float2bfloat16_rn(tile_hi[tx][ty + 8 * i]);
+            const __nv_bfloat16 bl = __float2bfloat16_rn(tile_lo[tx][ty + 8 * i]);
+            for (int sft = 0; sft < shifts; ++sft) {
+                // copy sft of a 3-shift set holds x shifted by dw = sft - 1 along the row: copy[q] = x[q + dw]
+                const long long q = shifts == 3 ? p - (sft - 1) : p;
+                const size_t o = (static_cast<size_t>(sft) * c + cc) * k_pad + q;
+                dst[o] = bh;
+                if (planes == 2) dst[plane_stride + o] = bl;
+            }
         }
     }
 }
@@ -691,25 +702,28 @@ extern "C" int32_t stemseg_to_planes(const float* x, int64_t elems, void* dst_pl
 }
 
 extern "C" int64_t stemseg_transposed_row_length(int32_t t, int32_t h, int32_t w, int32_t pad) {
-    const long long k = 1ll * (t + 2 * pad) * (h + 2 * pad) * (w + 2 * pad);
+    const long long k = 1ll * (t + 2 * pad) * (h + 2 * pad) * padded_row_pitch(w, pad);
     return (k + 63) / 64 * 64;          // multiple of the K chunk; the tail stays zero
 }
 
 extern "C" int32_t stemseg_transpose_pad(const void* src, int32_t src_is_planes, int32_t t, int32_t h, int32_t w,
-                                         int32_t c, int32_t pad, void* dst_planes, int32_t planes, void* stream_) {
+                                         int32_t c, int32_t pad, int32_t shifts, void* dst_planes, int32_t planes,
+                                         void* stream_) {
     SS_REQUIRE(src && dst_planes, "transpose_pad: null pointer");
+    SS_REQUIRE(shifts == 1 || (shifts == 3 && pad == 1), "transpose_pad: shifts must be 1, or 3 with pad 1");
     SS_REQUIRE(t >= 1 && h >= 1 && w >= 1 && c >= 1 && (pad == 0 || pad == 1), "transpose_pad: bad shape");
     SS_REQUIRE(planes == 1 || planes == 2, "transpose_pad: planes must be 1 or 2");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const long long k_pad = stemseg_transposed_row_length(t, h, w, pad);
-    SS_CUDA_OK(cudaMemsetAsync(dst_planes, 0, static_cast<size_t>(planes) * c * k_pad * 2, stream));
+    SS_CUDA_OK(cudaMemsetAsync(dst_planes, 0, static_cast<size_t>(planes) * shifts * c * k_pad * 2, stream));
     const long long spatial = 1ll * t * h * w;
     dim3 grid(static_cast<unsigned>((spatial + kTrV - 1) / kTrV), (c + kTrC - 1) / kTrC);
     if (src_is_planes)
-        transpose_pad_kernel<true><<<grid, 256, 0, stream>>>(src, t, h, w, c, pad, k_pad, static_cast<size_t>(spatial) * c,
+        transpose_pad_kernel<true><<<grid, 256, 0, stream>>>(src, t, h, w, c, pad, shifts, k_pad,
+                                                             static_cast<size_t>(spatial) * c,
                                                              static_cast<__nv_bfloat16*>(dst_planes), planes);
     else
-        transpose_pad_kernel<false><<<grid, 256, 0, stream>>>(src, t, h, w, c, pad, k_pad, 0,
+        transpose_pad_kernel<false><<<grid, 256, 0, stream>>>(src, t, h, w, c, pad, shifts, k_pad, 0,
                                                               static_cast<__nv_bfloat16*>(dst_planes), planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;

@@ -46,7 +46,8 @@ struct ConvTcParams {
     // ---- wgrad mode (backward_ops.cu): plain K-major GEMM out[m][n] = sum_k A[m][k] B[n][k + b_k_offset[slice]] over the
     // zero-padded transposed planes; slice = filter tap, K range additionally split over k_splits CTAs ---------------
     int wgrad_mode;
-    int b_k_offset[27];
+    int b_k_offset[27];        // (dt*hp + dh)*pitch: a multiple of 8 elements (TMA needs a 16-byte aligned inner coordinate)
+    int b_row_offset[27];      // (dw + 1)*cin: the dw shift selects one of three pre-shifted copies of the B rows
     int k_splits;              // >= 1
     int k_chunks_total;        // K chunks of the whole reduction (cin / BLOCK_K in normal mode)
     int tiles_per_cta;         // 0: persistent (tile = blockIdx.x + k*gridDim.x); >0: CTA b owns tiles [b*tpc, (b+1)*tpc)
@@ -260,12 +261,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_chunks = p.cin / BLOCK_K;
-    const int chunks_per_split = (k_chunks + p.k_splits - 1) / p.k_splits;      // only k_splits > 1 in wgrad mode
+    // wgrad mode: K range of split s = chunks [s*k_chunks/k_splits, (s+1)*k_chunks/k_splits) (never empty: the host keeps
+    // k_splits <= k_chunks)
+    auto split_begin = [&](int ksplit) -> int {
+        return static_cast<int>(static_cast<long long>(ksplit) * k_chunks / p.k_splits);
+    };
     auto k_blocks_of = [&](const TileCoord& tc) -> int {
         if (p.k_splits == 1) return p.taps_per_slice * k_chunks;
-        const int begin = tc.ksplit * chunks_per_split;
-        const int end = begin + chunks_per_split < k_chunks ? begin + chunks_per_split : k_chunks;
-        return end > begin ? end - begin : 0;
+        return split_begin(tc.ksplit + 1) - split_begin(tc.ksplit);
     };
     int tile_first = blockIdx.x, tile_last = p.num_tiles, tile_step = gridDim.x;
     if (p.tiles_per_cta > 0) {
@@ -314,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                     int tap = tc.slice * p.taps_per_slice + kb / k_chunks, c0 = (kb % k_chunks) * BLOCK_K;
                     if (p.wgrad_mode) {
                         tap = 0;
-                        c0 = (tc.ksplit * chunks_per_split + kb) * BLOCK_K;
+                        c0 = (split_begin(tc.ksplit) + kb) * BLOCK_K;
                     }
                     int dt = 0, dh = 0, dw = 0;
                     if (p.ntaps == 27) {
@@ -330,8 +333,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                         tma_load_5d(&a_map1, full_bar + stage, st + A_BYTES, c0, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n);
                     uint8_t* sb = st + PLANES * A_BYTES;
                     const int kcoord = p.wgrad_mode ? c0 + p.b_k_offset[tc.slice] : tap * p.cin + c0;
-                    tma_load_2d(&b_map0, full_bar + stage, sb, kcoord, tc.n_tile * BLOCK_N);
-                    if (PLANES == 2) tma_load_2d(&b_map1, full_bar + stage, sb + B_BYTES, kcoord, tc.n_tile * BLOCK_N);
+                    const int brow = tc.n_tile * BLOCK_N + (p.wgrad_mode ? p.b_row_offset[tc.slice] : 0);
+                    tma_load_2d(&b_map0, full_bar + stage, sb, kcoord, brow);
+                    if (PLANES == 2) tma_load_2d(&b_map1, full_bar + stage, sb + B_BYTES, kcoord, brow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -799,10 +803,23 @@ extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const voi
     return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, nullptr, s, max_ctas, stream_, &head);
 }
 
-extern "C" int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t kernel_size) {
+namespace {
+int wgrad_block_k(int cin, int planes) { return planes == 2 && block_n_for(cin) == 256 ? 32 : 64; }
+long long wgrad_k_pad(int t, int h, int w, int kernel_size) {
+    const int pad = kernel_size == 3 ? 1 : 0;
+    const int pitch = pad ? (w + 2 + 7) / 8 * 8 : w;                      // backward_ops.cu: padded_row_pitch
+    const long long k_true = 1ll * (t + 2 * pad) * (h + 2 * pad) * pitch;
+    return (k_true + 63) / 64 * 64;
+}
+}  // namespace
+
+extern "C" int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t t, int32_t h, int32_t w,
+                                          int32_t kernel_size, int32_t planes) {
     const int taps = kernel_size == 3 ? 27 : 1;
     const long long tiles = 1ll * ((cout + kBlockM - 1) / kBlockM) * (cin / block_n_for(cin)) * taps;
-    long long k = (3ll * device_sm_count() + tiles - 1) / tiles;
+    long long k = (3ll * device_sm_count() + tiles - 1) / tiles;          // aim at ~3 CTAs' worth of tiles per SM
+    const long long k_chunks = wgrad_k_pad(t, h, w, kernel_size) / wgrad_block_k(cin, planes);
+    if (k > k_chunks) k = k_chunks;                                       // every split owns at least one K chunk
     if (k < 1) k = 1;
     if (k > 32) k = 32;
     return static_cast<int32_t>(k);
@@ -822,9 +839,11 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
     if (rc != STEMSEG_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int pad = kernel_size == 3 ? 1 : 0;
-    const long long k_true = 1ll * (t + 2 * pad) * (h + 2 * pad) * (w + 2 * pad);
-    const long long k_pad = (k_true + 63) / 64 * 64;
+    const long long k_pad = wgrad_k_pad(t, h, w, kernel_size);
     SS_REQUIRE(k_pad < 0x7FFFFFFFll, "conv3d_wgrad: volume too large");
+    SS_REQUIRE(k_splits <= k_pad / wgrad_block_k(cin, planes),
+               "conv3d_wgrad: k_splits %d exceeds the %lld K chunks of this volume (use stemseg_wgrad_k_splits)", k_splits,
+               k_pad / wgrad_block_k(cin, planes));
 
     ConvTcParams p;
     p.n = 1; p.t = 1; p.h = 1; p.w = cout;                 // GEMM rows = output channels of the convolution
@@ -841,10 +860,12 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
     p.slice_stride = static_cast<size_t>(cout) * cin;
     p.k_splits = k_splits;
     p.wgrad_mode = 1;
-    const int hp = h + 2 * pad, wp = w + 2 * pad;
+    const int hp = h + 2 * pad, pitch = pad ? (w + 2 + 7) / 8 * 8 : w;
+    const int shifts = kernel_size == 3 ? 3 : 1;
     for (int tap = 0; tap < 27; ++tap) {
         const int dt = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
-        p.b_k_offset[tap] = kernel_size == 3 ? (dt * hp + dh) * wp + dw : 0;
+        p.b_k_offset[tap] = kernel_size == 3 ? (dt * hp + dh) * pitch : 0;
+        p.b_row_offset[tap] = kernel_size == 3 ? (dw + 1) * cin : 0;
     }
     const long long tiles = 1ll * p.tiles_w * p.n_tiles_n * p.k_slices * p.k_splits;
     p.num_tiles = static_cast<int>(tiles);
@@ -858,10 +879,9 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
     p.head_j = 0;
     p.k_chunks_total = 0;
 
-    int block_k = 64;
-    if (planes == 2 && block_n == 256) block_k = 32;
+    const int block_k = wgrad_block_k(cin, planes);
     const size_t a_plane_bytes = static_cast<size_t>(cout) * k_pad * 2;
-    const size_t b_plane_bytes = static_cast<size_t>(cin) * k_pad * 2;
+    const size_t b_plane_bytes = static_cast<size_t>(shifts) * cin * k_pad * 2;
     CUtensorMap maps[4];
     const uint8_t* a = static_cast<const uint8_t*>(dyT_planes);
     const uint8_t* b = static_cast<const uint8_t*>(xT_planes);
@@ -869,7 +889,8 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
         const int src = pl < planes ? pl : 0;
         rc = encode_act_map(&maps[pl], a + src * a_plane_bytes, p, block_k);
         if (rc != STEMSEG_OK) return rc;
-        rc = encode_weight_map(&maps[2 + pl], b + src * b_plane_bytes, k_pad, cin, block_k, block_n);
+        rc = encode_weight_map(&maps[2 + pl], b + src * b_plane_bytes, k_pad, static_cast<int64_t>(shifts) * cin, block_k,
+                               block_n);
         if (rc != STEMSEG_OK) return rc;
     }
     if (planes == 2)
