@@ -34,8 +34,12 @@ OFFSET_CHANNELS = {"xy": "yx", "ff": "", "xyt": "tyx", "xyf": "yx", "xytf": "tyx
                    "xyfff": "yx"}
 
 
-def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None):
-    """conv3x3x3(pad 1) -> GroupNorm -> ReLU -> [AvgPool3d(3, (2,1,1), 1)]   (embedding_decoder.py:21-24)."""
+def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None, relu_masks=None):
+    """conv3x3x3(pad 1) -> GroupNorm -> ReLU -> [AvgPool3d(3, (2,1,1), 1)]   (embedding_decoder.py:21-24).
+
+    relu_masks (gradient tests only): {"<block>.<conv_idx>": 0/1 tensor} replaces the ReLU's own sign decision by a
+    given one, so that two implementations whose pre-activations differ by rounding are differentiated along the
+    SAME linear piece (the ReLU kink makes the gradient discontinuous in elements that round across zero)."""
     w, b = sd["%s.%d.weight" % (prefix, conv_idx)], sd["%s.%d.bias" % (prefix, conv_idx)]
     y = F.conv3d(x, w, b, stride=1, padding=1)
     if trace is not None:
@@ -43,7 +47,11 @@ def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None):
     if gn_groups:
         y = F.group_norm(y, gn_groups, sd["%s.%d.weight" % (prefix, conv_idx + 1)],
                          sd["%s.%d.bias" % (prefix, conv_idx + 1)], eps=1e-5)
-    y = F.relu(y)
+    key = "%s.%d" % (prefix, conv_idx)
+    if relu_masks is not None and key in relu_masks:
+        y = y * relu_masks[key].to(y.dtype)
+    else:
+        y = F.relu(y)
     if pooled:
         y = F.avg_pool3d(y, 3, stride=(2, 1, 1), padding=1)      # count_include_pad=True -> always /27
     if trace is not None:
@@ -51,7 +59,7 @@ def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None):
     return y
 
 
-def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None):
+def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None, relu_masks=None):
     """Shared trunk of all three heads -> [N, c3, T, H/4, W/4] (embedding_decoder.py:109-129)."""
     pools = POOL_SLOTS[num_frames]
     tscale = TEMPORAL_SCALES[num_frames]
@@ -59,7 +67,8 @@ def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None):
     for (name, stages), f in zip(BLOCKS, feats_32_16_8_4):
         y = f
         for j in range(stages):
-            y = conv_stage(y, sd, name, 4 * j, gn_groups, pools[j] and name not in UNPOOLED_BLOCKS, trace)    # Sequential indices 0,4,8
+            y = conv_stage(y, sd, name, 4 * j, gn_groups, pools[j] and name not in UNPOOLED_BLOCKS, trace,
+                           relu_masks)    # Sequential indices 0,4,8
         branch.append(y)
     x = branch[0]
     for k, merge in enumerate(MERGES):
@@ -82,9 +91,9 @@ def coordinate_grid(t, h, w, time_scale=1.0):
 
 
 def embedding_head(sd, feats, num_frames, embedding_size, dim_mode, tanh_activation=True, seediness_output=True,
-                   gn_groups=32, trace=None):
+                   gn_groups=32, trace=None, relu_masks=None):
     """-> cat(embeddings, variances[, seediness]) [N, E + (E - free) + {0,1}, T, H/4, W/4]."""
-    x = trunk(sd, feats, num_frames, gn_groups, trace)
+    x = trunk(sd, feats, num_frames, gn_groups, trace, relu_masks)
     emb = F.conv3d(x, sd["conv_embedding.weight"], None)
     assert emb.shape[1] == EMBEDDING_DIMS[dim_mode] == embedding_size
     if tanh_activation:
@@ -103,13 +112,14 @@ def embedding_head(sd, feats, num_frames, embedding_size, dim_mode, tanh_activat
     return torch.cat(outs, dim=1)
 
 
-def seediness_head(sd, feats, num_frames, gn_groups=32, trace=None):
-    return F.conv3d(trunk(sd, feats, num_frames, gn_groups, trace), sd["conv_out.weight"], None).sigmoid()
+def seediness_head(sd, feats, num_frames, gn_groups=32, trace=None, relu_masks=None):
+    return F.conv3d(trunk(sd, feats, num_frames, gn_groups, trace, relu_masks), sd["conv_out.weight"], None).sigmoid()
 
 
-def semseg_head(sd, feats_4_8_16_32, num_frames, gn_groups=32, trace=None):
+def semseg_head(sd, feats_4_8_16_32, num_frames, gn_groups=32, trace=None, relu_masks=None):
     """Input list arrives highest resolution first and is reversed (semseg_decoder.py:94)."""
-    return F.conv3d(trunk(sd, feats_4_8_16_32[::-1], num_frames, gn_groups, trace), sd["conv_out.weight"], None)
+    return F.conv3d(trunk(sd, feats_4_8_16_32[::-1], num_frames, gn_groups, trace, relu_masks), sd["conv_out.weight"],
+                    None)
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -19,6 +19,11 @@ from stemseg_b200 import _lib
 from stemseg_b200 import decoder as D
 
 
+# tests set this to a list to receive the saved forward state of every training_forward call (to read the ReLU sign
+# decisions of the CUDA forward)
+DEBUG_SAVED = None
+
+
 def _check(rc):
     _lib.check(rc)
 
@@ -67,6 +72,8 @@ def training_forward(head, feats):
             out = D.head_output(z, y_low, tscale[k], out_spec)
     saved["out_spec"] = out_spec
     D.KEEP = []
+    if DEBUG_SAVED is not None:
+        DEBUG_SAVED.append(saved)
     return out, saved
 
 
