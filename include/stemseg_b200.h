@@ -34,6 +34,7 @@ extern "C" {
 
 #define STEMSEG_MAX_EMBEDDING_DIMS 16
 #define STEMSEG_MAX_INSTANCES 64
+#define STEMSEG_MAX_LOSS_INSTANCES 32
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* stemseg_last_error(void);
@@ -332,6 +333,34 @@ int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_planes, int3
 /* sum the slices into the state_dict layout dst[cout][cin_total][taps] at input-channel offset cin_begin */
 int32_t stemseg_wgrad_reduce(const float* slices, int32_t n_slices, int32_t cout, int32_t ntaps, int32_t cin, float* dst,
                              int32_t cin_total, int32_t cin_begin, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Embedding loss of one training sequence: loss terms AND the gradient wrt the head output in one call
+ *   replaces EmbeddingLoss.forward / compute_prob_map / compute_bandwidth_smoothness_loss
+ *                                                     stemseg/modeling/losses/embedding_loss.py:35-185
+ *            lovasz_hinge_flat / lovasz_grad          stemseg/modeling/losses/_lovasz.py:139-157, :18-31
+ *            and torch autograd through them          stemseg/training/main.py:195-201
+ * head_out [E+V][voxels] fp32 channels-first (embedding rows then variance rows, V = E - n_free_dims), seediness
+ * [voxels], masks [n_instances][voxels] uint8 (0 / non-zero), ignore [voxels] uint8 or NULL -- all device pointers.
+ * Per kept instance: masked mean centre and mean activated bandwidth (10 exp(var), free dims 1/std^2), Gaussian
+ * probability of EVERY voxel, Lovasz hinge (full descending sort of the hinge errors, done by an on-device
+ * bitonic sort of 64-bit keys), seediness regression to the detached probability, variance smoothness.
+ * One sequence per call (the reference trains with MAX_SAMPLES_PER_GPU = 1, defaults.yaml:20); quirks preserved:
+ * empty instances are dropped but kept slot n is paired with masks[n] (embedding_loss.py:83-87,128); no background
+ * voxel at all -> NaN seediness term (mean of an empty tensor).
+ * Outputs (device): losses[4] = {total (weighted, x w), lovasz, variance_smoothness, seediness};
+ * d_head_out [E+V][voxels] and d_seediness [voxels] = gradient of losses[0] (every element written).
+ * No host synchronisation; reductions accumulate in double (order-independent to ~1e-16).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t stemseg_embedding_loss_workspace_bytes(int64_t voxels, int32_t n_instances);
+int32_t stemseg_embedding_loss(const float* head_out, const float* seediness, const uint8_t* masks,
+                               const uint8_t* ignore, int64_t voxels, int32_t n_instances, int32_t embedding_dims,
+                               int32_t n_free_dims, const float* free_dim_stds /* host, n_free_dims */,
+                               float w_lovasz, float w_variance_smoothness, float w_seediness, float w, float* losses,
+                               float* d_head_out, float* d_seediness, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* x[i] *= *scalar (scalar in device memory: chain-rule factor of loss.backward() without a host round trip) */
+int32_t stemseg_scale_by_device_scalar(float* x, int64_t n, const float* scalar, void* stream);
 
 #ifdef __cplusplus
 }

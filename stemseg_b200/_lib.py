@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -93,6 +93,11 @@ PROTOTYPES = {
                                        c_int32, c_int32, c_void_p, c_void_p]),
     "stemseg_wgrad_reduce": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_void_p]),
+    "stemseg_embedding_loss_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "stemseg_embedding_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                         ctypes.POINTER(c_float), c_float, c_float, c_float, c_float, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_scale_by_device_scalar": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "stemseg_conv3d_auto_split": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_float,
@@ -121,12 +126,6 @@ KERNEL_LAUNCHES = [0]
 KERNELS_PER_CALL = {
     "stemseg_seq_cluster": 1, "stemseg_fg_compact": 3, "stemseg_fg_compact_threshold": 3, "stemseg_fg_gather": 1, "stemseg_fg_compact_mean_threshold": 3, "stemseg_frame_accumulate": 1,
     "stemseg_fg_gather_upsampled": 1,
-    "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
-                                               c_void_p, c_void_p, c_void_p]),
-    "stemseg_relabel_lut": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
-    "stemseg_rank_map_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
-    "stemseg_mask_writeback": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                         c_int32, c_void_p, c_void_p]),
     "stemseg_pack_activation": 1, "stemseg_pack_conv_weight": 1, "stemseg_conv3d_bf16_planes": 1,
     "stemseg_group_norm_stats": 2, "stemseg_group_norm_finalize": 1, "stemseg_norm_relu_pool": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
     "stemseg_head_lowres": 1, "stemseg_conv1x1_head_output": 1,
@@ -135,6 +134,8 @@ KERNELS_PER_CALL = {
     "stemseg_pack_conv_weight_dgrad": 1, "stemseg_head_backward": 3, "stemseg_upsample_transpose": 1,
     "stemseg_pool_relu_backward": 1, "stemseg_group_norm_backward": 3, "stemseg_channel_sum": 2,
     "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
+    "stemseg_scale_by_device_scalar": 1,
+    # stemseg_embedding_loss launches a shape-dependent number of kernels: counted by losses.py
 }
 
 

@@ -1,0 +1,93 @@
+"""GPU: csrc/embedding_loss.cu through stemseg_b200.losses.EmbeddingLoss against the reference fixtures and the
+float64 oracle.  Tolerances: loss terms 1e-5 relative, gradient 1e-4 norm-wise (fp32 arithmetic, double reductions)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import loss_cases as lc
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _criterion(case):
+    from stemseg_b200.losses import EmbeddingLoss
+    return EmbeddingLoss(4, embedding_size=case["embedding_size"], nbr_free_dims=case["n_free"],
+                         free_dim_stds=lc.FREE_DIM_STDS[case["n_free"]], WEIGHT_VARIANCE_SMOOTHNESS=10.0,
+                         WEIGHT_LOVASZ=1.0, WEIGHT_REGULARIZATION=0.001, WEIGHT_SEEDINESS=1.0, WEIGHT=1.0)
+
+
+def _run_cuda(case, device, scale=1.0):
+    from stemseg_b200 import losses as L
+    crit = _criterion(case)
+    out = case["out"].to(device).requires_grad_(True)
+    od = {}
+    total = crit(out, [{"masks": case["masks"].to(device), "ignore_masks": case["ignore"].to(device)}], od)
+    assert od[L.OUTPUT_OPTIMIZATION_LOSSES][L.LOSS_EMBEDDING] is total
+    (total * scale).backward()
+    torch.cuda.synchronize()
+    got = {"total": float(total), "lovasz": float(od[L.OUTPUT_OTHERS][L.LOSS_LOVASZ]),
+           "variance_smoothness": float(od[L.OUTPUT_OTHERS][L.LOSS_VARIANCE_SMOOTHNESS]),
+           "seediness": float(od[L.OUTPUT_OTHERS][L.LOSS_SEEDINESS])}
+    return got, out.grad.detach().cpu()
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "loss_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(lc.case_table()))
+def test_matches_reference_fixture(name, golden, cuda_device):
+    case = lc.build_case(name)
+    got, grad = _run_cuda(case, cuda_device)
+    for key, val in got.items():
+        ref = float(golden["%s/%s" % (name, key)])
+        assert abs(val - ref) <= LOSS_TOL * max(abs(ref), 1e-3), (key, val, ref)
+    ref_grad = torch.from_numpy(golden["%s/grad" % name])
+    if float(ref_grad.norm()) == 0.0:
+        assert float(grad.abs().max()) == 0.0
+    else:
+        assert float((grad - ref_grad).norm() / ref_grad.norm()) <= GRAD_TOL
+        # per output group too (embedding / variance / seediness rows have very different scales)
+        e, v = case["embedding_size"], case["embedding_size"] - case["n_free"]
+        for a, b in ((0, e), (e, e + v), (e + v, e + v + 1)):
+            r = ref_grad[:, a:b]
+            assert float((grad[:, a:b] - r).norm() / max(float(r.norm()), 1e-30)) <= GRAD_TOL
+
+
+def test_training_size_against_float64_oracle(cuda_device):
+    """BASELINE configs[4] geometry: 8 x 384 x 640 clip -> 8 x 96 x 160 embedding grid (122 880 voxels: the bitonic
+    sort runs on 131 072 padded keys, 32 shared-memory chunks + 15 global steps)."""
+    case = lo.seeded_case(seed=99, t=8, h=96, w=160, embedding_size=4, n_free=2, instances=3)
+    got, grad = _run_cuda(case, cuda_device)
+    out64 = case["out"].double().requires_grad_(True)
+    ref = lo.loss_from_head_output(out64, case["masks"], case["ignore"], 4, 2, lc.FREE_DIM_STDS[2], **lc.WEIGHTS)
+    ref["total"].backward()
+    for key, val in got.items():
+        assert abs(val - float(ref[key])) <= LOSS_TOL * max(abs(float(ref[key])), 1e-3), (key, val, float(ref[key]))
+    assert float((grad.double() - out64.grad).norm() / out64.grad.norm()) <= GRAD_TOL
+
+
+def test_chain_rule_factor_is_applied_on_device(cuda_device):
+    case = lc.build_case("xyff_3inst")
+    _, g1 = _run_cuda(case, cuda_device, 1.0)
+    _, g2 = _run_cuda(case, cuda_device, 0.25)         # ModelOutputManager divides by the accumulation interval
+    assert torch.allclose(g2, g1 * 0.25, rtol=1e-6, atol=0)
+
+
+def test_rejects_cpu_and_batches(cuda_device):
+    case = lc.build_case("xyt_2inst")
+    crit = _criterion(case)
+    with pytest.raises(ValueError):
+        crit(case["out"].clone().requires_grad_(True), [{"masks": case["masks"], "ignore_masks": case["ignore"]}], {})
+    two = torch.cat([case["out"], case["out"]], 0).to(cuda_device)
+    with pytest.raises(NotImplementedError):
+        crit(two, [{"masks": case["masks"], "ignore_masks": case["ignore"]}] * 2, {})
+    with pytest.raises(AssertionError):
+        crit(case["out"][:, :3].to(cuda_device), [{"masks": case["masks"], "ignore_masks": case["ignore"]}], {})
