@@ -592,6 +592,245 @@ def run_video64(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# configs[4]: data-parallel training step of the heads (one 8x384x640 clip per GPU per step)
+# ------------------------------------------------------------------------------------------------------------------
+TRAIN_T, TRAIN_H, TRAIN_W = 8, 384, 640
+TRAIN_WORKLOAD = "configs[4]: DDP training step, one 8x384x640 clip per GPU: embedding + seediness heads " \
+                 "([256,256,128,128]) forward, embedding loss (Lovasz + seediness + variance smoothness, 3 instances), " \
+                 "backward to features and parameters, gradient all-reduce, SGD-Nesterov"
+TRAIN_GFLOP_PER_CLIP = 3 * 2 * 334.7          # fwd + dgrad + wgrad of two heads (334.7 GFLOP / head)
+
+
+def make_train_inputs(seed):
+    """Synthetic FPN pyramid + targets (three moving ellipses) at the embedding resolution."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h4, w4 = TRAIN_H // 4, TRAIN_W // 4
+    feats = [torch.randn(1, IN_CH, TRAIN_T, TRAIN_H // s, TRAIN_W // s, generator=g) for s in (32, 16, 8, 4)]
+    yy, xx = torch.meshgrid(torch.arange(h4, dtype=torch.float32), torch.arange(w4, dtype=torch.float32), indexing="ij")
+    masks = torch.zeros(3, TRAIN_T, h4, w4, dtype=torch.uint8)
+    taken = torch.zeros(TRAIN_T, h4, w4, dtype=torch.bool)
+    for i, (cy, cx, ry, rx, vy, vx) in enumerate(((0.3, 0.3, 0.15, 0.12, 0.01, 0.02), (0.6, 0.65, 0.2, 0.15, -0.01, 0.01),
+                                                  (0.75, 0.25, 0.1, 0.1, 0.0, -0.015))):
+        for f in range(TRAIN_T):
+            m = ((yy - (cy + vy * f) * h4) / (ry * h4)) ** 2 + ((xx - (cx + vx * f) * w4) / (rx * w4)) ** 2 <= 1.0
+            m &= ~taken[f]
+            masks[i, f] = m
+            taken[f] |= m
+    ignore = torch.rand(TRAIN_T, h4, w4, generator=g) < 0.02
+    return feats, masks, ignore
+
+
+def train_reference_step(state, feats, masks, ignore):
+    """The reference's CPU training step for the heads, restated with the oracles (torch-CPU fp32 autograd through
+    the same ATen ops as the reference modules + torch.optim.SGD)."""
+    import torch
+    from oracle import decoder_oracle as do
+    from oracle import loss_oracle as lo
+    emb_sd, seed_sd, opt = state
+    opt.zero_grad()
+    f = [x.clone().requires_grad_(True) for x in feats]
+    out = torch.cat((do.embedding_head(emb_sd, f, TRAIN_T, 4, "xyff", True, False),
+                     do.seediness_head(seed_sd, f, TRAIN_T)), dim=1)
+    losses = lo.loss_from_head_output(out, masks, ignore, 4, 2, [0.3, 0.3], w_lovasz=1.0, w_variance_smoothness=10.0,
+                                      w_seediness=1.0, w=1.0)
+    losses["total"].backward()
+    opt.step()
+    return float(losses["total"])
+
+
+def build_train_reference():
+    import torch
+    emb_sd, seed_sd = build_cpu_reference()
+    emb_sd = {k: (v.clone().requires_grad_(True) if v.dim() > 0 else v) for k, v in emb_sd.items()}
+    seed_sd = {k: v.clone().requires_grad_(True) for k, v in seed_sd.items()}
+    params = [v for v in list(emb_sd.values()) + list(seed_sd.values()) if v.requires_grad]
+    opt = torch.optim.SGD(params, 1e-3, 0.9, weight_decay=1e-4, nesterov=True)
+    return emb_sd, seed_sd, opt
+
+
+def run_train_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    feats, masks, ignore = make_train_inputs(0)
+    state = build_train_reference()
+    for _ in range(max(1, min(args.warmup, 1))):
+        train_reference_step(state, feats, masks, ignore)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_reference_step(state, feats, masks, ignore)
+    dt = time.perf_counter() - t0
+    value = steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "train_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD, "timing": "host wall clock"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d full training steps (oracle port: torch-CPU fp32 autograd + SGD)" % steps},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_train(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    from stemseg_b200 import _lib, decoder, heads
+    from stemseg_b200.losses import EmbeddingLoss
+    from stemseg_b200.training import DecoderTrainer
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    _lib.check(_lib.load().stemseg_check_device())
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    torch.manual_seed(42)
+    norm = lambda c: nn.GroupNorm(32, c)       # noqa: E731
+    emb = heads.EmbeddingHead(IN_CH, list(INTER), 4, True, False, "xyff", NormType=norm, num_frames=TRAIN_T,
+                              precision=args.precision).to(device)
+    seedh = heads.SeedinessHead(IN_CH, list(INTER), NormType=norm, num_frames=TRAIN_T,
+                                precision=args.precision).to(device)
+    crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3], weight_variance_smoothness=10.0,
+                         weight_lovasz=1.0, weight_regularization=0.001, weight_seediness=1.0, weight=1.0)
+    trainer = DecoderTrainer({"embedding": emb, "seediness": seedh}, crit)
+    feats_cpu, masks, ignore = make_train_inputs(rank)
+    host_feats = [f.pin_memory() for f in feats_cpu]
+    dev_feats = [f.to(device).requires_grad_(True) for f in host_feats]
+    targets = [{"masks": masks.to(device), "ignore_masks": ignore.to(device)}]
+    host_targets = [{"masks": masks.pin_memory(), "ignore_masks": ignore.to(torch.uint8).pin_memory()}]
+
+    def step_resident():
+        for f in dev_feats:
+            f.grad = None
+        return trainer.step(dev_feats, targets)
+
+    def step_e2e():
+        f = [x.to(device, non_blocking=True).requires_grad_(True) for x in host_feats]
+        t = [{"masks": host_targets[0]["masks"].to(device, non_blocking=True),
+              "ignore_masks": host_targets[0]["ignore_masks"].to(device, non_blocking=True)}]
+        out = trainer.step(f, t)
+        return float(out["optimization_losses"]["embedding_loss"])       # D2H read of the loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.KERNEL_LAUNCHES[0] = 0
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.KERNEL_LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # phase breakdown (rank 0, informational): forward / loss / backward / exchange+SGD, CUDA events
+    phases = {}
+    if rank == 0:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for flat in trainer.flats:
+            flat.zero_grad()
+        for f in dev_feats:
+            f.grad = None
+        torch.cuda.synchronize()
+        ev[0].record()
+        out = torch.cat((emb(dev_feats), seedh(dev_feats)), dim=1)
+        ev[1].record()
+        od = {}
+        loss = crit(out, targets, od)
+        ev[2].record()
+        loss.backward()
+        ev[3].record()
+        trainer.exchange.finish()
+        from stemseg_b200.training import sgd_step
+        for flat, mod in zip(trainer.flats, (emb, seedh)):
+            sgd_step(flat, trainer.lr, trainer.momentum, trainer.weight_decay, trainer.nesterov, 1.0 / world)
+            mod.invalidate_packed_weights()
+        ev[4].record()
+        torch.cuda.synchronize()
+        for name, i in (("forward_ms", 0), ("loss_ms", 1), ("backward_ms", 2), ("exchange_sgd_ms", 3)):
+            phases[name] = ev[i].elapsed_time(ev[i + 1])
+        # per-launch conv timing of one eager step (forward, dgrad and wgrad all go through conv_tc_kernel)
+        decoder.PROFILE_EVENTS = []
+        step_resident()
+        torch.cuda.synchronize()
+        conv_ms = sum(a.elapsed_time(b) for _, a, b in decoder.PROFILE_EVENTS)
+        phases["conv_launches"] = len(decoder.PROFILE_EVENTS)
+        phases["conv_ms"] = conv_ms
+        decoder.PROFILE_EVENTS = None
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    clips = args.steps * world
+    value = clips / (ms_total * 1e-3)
+    ms_step = ms_total / args.steps
+    achieved = TRAIN_GFLOP_PER_CLIP / ms_step            # GFLOP / ms = TFLOP/s, per GPU
+    products = 3 if args.precision == "fp32" else 1
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        state = build_train_reference()
+        train_reference_step(state, feats_cpu, masks, ignore)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 10):
+            train_reference_step(state, feats_cpu, masks, ignore)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": reps / dt, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "%d full training steps after warm-up (oracle port: torch-CPU fp32 autograd + SGD)" % reps}
+    h2d = sum(f.numel() * 4 for f in host_feats) + masks.numel() + ignore.numel()
+    print(json.dumps({
+        "metric": "train_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD, "precision": args.precision, "global_batch": world,
+                   "l2": "inputs + saved activations larger than L2 (pyramid 167 MB, saved conv outputs > 1 GB per step)",
+                   "parallelism": "dp%d: per-head flat gradient all-reduce (NCCL, async, overlapped with the other "
+                                  "head's backward), mean folded into the fused SGD pass" % world},
+        "mvoxels_per_sec": value * TRAIN_T * TRAIN_H * TRAIN_W / 1e6,
+        "clocks": clocks,
+        "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "pinned host pyramid + targets copied in every step, loss read back every step"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "kernel": "whole training step (conv_tc_kernel forward + dgrad + wgrad dominate)",
+                     "algorithmic_gflop_per_step": TRAIN_GFLOP_PER_CLIP, "tensor_pipe_products_per_mac": products,
+                     "tensor_pipe_frac": achieved * products / peaks["bf16_tflops_sustained"],
+                     "peak_source": "%s bf16_tflops_sustained" % peaks["source"]},
+        "cpu_baseline": cpu_baseline, "phases": phases}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -600,8 +839,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="davis480p", choices=["davis480p", "cfg3", "video64"],
-                    help="davis480p = BASELINE configs[1] (the contract line); cfg3 / video64 = configs[2] / configs[3]")
+    ap.add_argument("--workload", default="davis480p", choices=["davis480p", "cfg3", "video64", "train"],
+                    help="davis480p = BASELINE configs[1] (the contract line); cfg3 / video64 / train = configs[2] / "
+                         "configs[3] / configs[4]")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -609,6 +849,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if args.workload == "train":
+            return run_train_reference(args, rank, world)
         run_reference_arm(args, rank, world)
         return
     if world != args.gpus:
@@ -619,6 +861,8 @@ def main():
         return run_cfg3(args, rank, local_rank, world)
     if args.workload == "video64":
         return run_video64(args, rank, local_rank, world)
+    if args.workload == "train":
+        return run_train(args, rank, local_rank, world)
     run_gpu_arm(args, rank, local_rank, world)
 
 

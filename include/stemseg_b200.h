@@ -362,6 +362,16 @@ int32_t stemseg_embedding_loss(const float* head_out, const float* seediness, co
 /* x[i] *= *scalar (scalar in device memory: chain-rule factor of loss.backward() without a host round trip) */
 int32_t stemseg_scale_by_device_scalar(float* x, int64_t n, const float* scalar, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused SGD step over a flat fp32 parameter buffer
+ *   replaces torch.optim.SGD(..., momentum, weight_decay, nesterov).step()   stemseg/training/utils.py:199-202,
+ *                                                                            stemseg/training/main.py:209
+ * g' = grad * grad_scale + weight_decay * p;  buf = momentum * buf + g';  p -= lr * (nesterov ? g' + momentum * buf : buf)
+ * grad_scale = 1 / world_size folds the data-parallel mean into the pass.  momentum_buf must start zeroed.
+ * ---------------------------------------------------------------------------------------------------------- */
+int32_t stemseg_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                         float weight_decay, float grad_scale, int32_t nesterov, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

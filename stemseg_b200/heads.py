@@ -111,6 +111,12 @@ class _SqueezeExpandTrunk(nn.Module):
             self._head_set = None
         return self._packed
 
+    def invalidate_packed_weights(self):
+        """Call after modifying parameters behind autograd's back (e.g. the fused optimiser kernel writes the flat
+        buffer the parameters are views of): the next forward / backward repacks the kernel-layout weights."""
+        self._packed = self._packed_key = self._head_set = None
+        self._dgrad_cache = None
+
     def _get_head_set(self):
         spec = self.head_spec()
         if getattr(self, "_head_set", None) is None:
