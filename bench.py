@@ -712,7 +712,7 @@ def run_train(args, rank, local_rank, world):
         t = [{"masks": host_targets[0]["masks"].to(device, non_blocking=True),
               "ignore_masks": host_targets[0]["ignore_masks"].to(device, non_blocking=True)}]
         out = trainer.step(f, t)
-        return float(out["optimization_losses"]["embedding_loss"])       # D2H read of the loss
+        return float(out["optimization_losses"]["embedding_loss"].detach())       # D2H read of the loss
 
     def barrier():
         torch.cuda.synchronize()

@@ -330,6 +330,13 @@ int32_t stemseg_wgrad_k_splits(int32_t cout, int32_t cin, int32_t t, int32_t h, 
 int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_planes, int32_t cout, int32_t cin, int32_t t,
                              int32_t h, int32_t w, int32_t kernel_size, int32_t planes, int32_t k_splits, float* slices,
                              void* stream);
+/* Direct weight gradient (the default): both operands stay NDHWC bf16 planes [P][1][t][h][w][C] (dy from
+ * stemseg_to_planes, x = the forward pass's input planes) and are consumed as MN-major tensor-core tiles; the tap
+ * shift / zero padding is a TMA coordinate on the x operand.  slices [k_splits][taps][cout][cin]. */
+int32_t stemseg_wgrad_direct_k_splits(int32_t cout, int32_t cin, int32_t t, int32_t h, int32_t w, int32_t kernel_size);
+int32_t stemseg_conv3d_wgrad_direct(const void* dy_planes, const void* x_planes, int32_t cout, int32_t cin, int32_t t,
+                                    int32_t h, int32_t w, int32_t kernel_size, int32_t planes, int32_t k_splits,
+                                    float* slices, void* stream);
 /* sum the slices into the state_dict layout dst[cout][cin_total][taps] at input-channel offset cin_begin */
 int32_t stemseg_wgrad_reduce(const float* slices, int32_t n_slices, int32_t cout, int32_t ntaps, int32_t cin, float* dst,
                              int32_t cin_total, int32_t cin_begin, int32_t accumulate, void* stream);

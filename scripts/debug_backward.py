@@ -175,9 +175,17 @@ def _wgrad(ksize, cin, cout, t, h, w):
     o.backward(g)
     xp = D.pack_activation(x, planes)
     dst = torch.empty(cout, cin, ksize ** 3, device=dev)
-    A._wgrad(ndhwc(g), xp, ksize, planes, dst, 0)
+    dy = ndhwc(g)
+    dyp = A._to_planes(dy, planes)
+    A._wgrad(dy, dyp, xp, ksize, planes, dst, 0)
     torch.cuda.synchronize()
-    print("wgrad k=%d cin=%d cout=%d %dx%dx%d" % (ksize, cin, cout, t, h, w), rel(dst.view_as(wt), wt.grad))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    A._wgrad(dy, dyp, xp, ksize, planes, dst, 0)
+    b.record()
+    torch.cuda.synchronize()
+    print("wgrad[%s] k=%d cin=%d cout=%d %dx%dx%d" % (A.WGRAD_MODE, ksize, cin, cout, t, h, w),
+          "rel %.3g" % rel(dst.view_as(wt), wt.grad), "%.1f us" % (1e3 * a.elapsed_time(b)))
 
 
 def op_wgrad():
@@ -189,6 +197,13 @@ def op_wgrad():
 def op_wgrad1():
     _wgrad(1, 32, 32, 2, 4, 8)
     _wgrad(1, 64, 96, 4, 12, 16)
+
+
+def op_wgradbig():
+    _wgrad(3, 128, 128, 4, 24, 40)
+    _wgrad(3, 256, 256, 4, 12, 20)
+    _wgrad(1, 256, 128, 8, 24, 40)
+    _wgrad(3, 256, 128, 8, 96, 160)
 
 
 OPS = {k[3:]: v for k, v in list(globals().items()) if k.startswith("op_")}

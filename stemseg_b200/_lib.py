@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -92,6 +92,9 @@ PROTOTYPES = {
     "stemseg_wgrad_k_splits": (c_int32, [c_int32] * 7),
     "stemseg_conv3d_wgrad": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_int32, c_void_p, c_void_p]),
+    "stemseg_wgrad_direct_k_splits": (c_int32, [c_int32] * 6),
+    "stemseg_conv3d_wgrad_direct": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                              c_int32, c_int32, c_void_p, c_void_p]),
     "stemseg_wgrad_reduce": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_void_p]),
     "stemseg_embedding_loss_workspace_bytes": (c_size_t, [c_int64, c_int32]),
@@ -137,6 +140,7 @@ KERNELS_PER_CALL = {
     "stemseg_pack_conv_weight_dgrad": 1, "stemseg_head_backward": 3, "stemseg_upsample_transpose": 1,
     "stemseg_pool_relu_backward": 1, "stemseg_group_norm_backward": 3, "stemseg_channel_sum": 2,
     "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
+    "stemseg_conv3d_wgrad_direct": 1,
     "stemseg_scale_by_device_scalar": 1, "stemseg_sgd_step": 1,
     # stemseg_embedding_loss launches a shape-dependent number of kernels: counted by losses.py
 }

@@ -13,11 +13,17 @@ Gradients flow to the four feature maps (so the torch backbone trains as usual) 
 all DistributedDataParallel needs: its gradient all-reduce hooks fire on the parameters' ``.grad`` as with the
 reference heads.  One sub-clip per call (batch 1), like the reference's MAX_SAMPLES_PER_GPU = 1 (defaults.yaml:20).
 """
+import os
+
 import torch
 
 from stemseg_b200 import _lib
 from stemseg_b200 import decoder as D
 
+
+# "direct": weight gradients from the NDHWC planes with MN-major tensor-core operands (stemseg_conv3d_wgrad_direct);
+# "transposed": the first implementation (zero-padded transposed copies, K-major operands), kept for cross-checking
+WGRAD_MODE = os.environ.get("STEMSEG_WGRAD", "direct")
 
 # tests set this to a list to receive the saved forward state of every training_forward call (to read the ReLU sign
 # decisions of the CUDA forward)
@@ -119,26 +125,35 @@ def _to_planes(x, planes):
     return D.Planes(dst, n, t, h, w, c)
 
 
-def _wgrad(dy, x_planes, kernel_size, planes, dst, cin_begin):
-    """dst[cout][cin_total][taps] (a parameter gradient in state_dict layout) <- wgrad(dy fp32 NDHWC, x Planes)."""
+def _wgrad(dy, dy_planes, x_planes, kernel_size, planes, dst, cin_begin):
+    """dst[cout][cin_total][taps] (a parameter gradient in state_dict layout) <- wgrad(dy [1,t,h,w,co], x Planes).
+
+    dy_planes: the same gradient as bf16 planes (shared with the dgrad convolution)."""
     lib = _lib.load()
     _, t, h, w, co = dy.shape
     ci = x_planes.c
     assert (x_planes.t, x_planes.h, x_planes.w) == (t, h, w)
-    pad = 1 if kernel_size == 3 else 0
     taps = 27 if kernel_size == 3 else 1
-    kp = lib.stemseg_transposed_row_length(t, h, w, pad)
     dev = dy.device
-    shifts = 3 if kernel_size == 3 else 1      # pre-shifted copies of x: TMA start coordinates must be 16-byte aligned
-    dy_t = _empty((planes, co, kp), torch.bfloat16, dev)
-    x_t = _empty((planes, shifts, ci, kp), torch.bfloat16, dev)
-    _check(lib.stemseg_transpose_pad(_lib.ptr(dy), 0, t, h, w, co, pad, 1, _lib.ptr(dy_t), planes, _lib.stream_ptr()))
-    _check(lib.stemseg_transpose_pad(_lib.ptr(x_planes.tensor), 1, t, h, w, ci, pad, shifts, _lib.ptr(x_t), planes,
-                                     _lib.stream_ptr()))
-    ks = lib.stemseg_wgrad_k_splits(co, ci, t, h, w, kernel_size, planes)
-    slices = _empty((ks, taps, co, ci), torch.float32, dev)
-    _check(lib.stemseg_conv3d_wgrad(_lib.ptr(dy_t), _lib.ptr(x_t), co, ci, t, h, w, kernel_size, planes, ks,
-                                    _lib.ptr(slices), _lib.stream_ptr()))
+    if WGRAD_MODE == "direct":
+        ks = lib.stemseg_wgrad_direct_k_splits(co, ci, t, h, w, kernel_size)
+        slices = _empty((ks, taps, co, ci), torch.float32, dev)
+        _check(lib.stemseg_conv3d_wgrad_direct(_lib.ptr(dy_planes.tensor), _lib.ptr(x_planes.tensor), co, ci, t, h, w,
+                                               kernel_size, planes, ks, _lib.ptr(slices), _lib.stream_ptr()))
+    else:
+        pad = 1 if kernel_size == 3 else 0
+        kp = lib.stemseg_transposed_row_length(t, h, w, pad)
+        shifts = 3 if kernel_size == 3 else 1      # pre-shifted copies of x: TMA start coordinates must be 16-byte aligned
+        dy_t = _empty((planes, co, kp), torch.bfloat16, dev)
+        x_t = _empty((planes, shifts, ci, kp), torch.bfloat16, dev)
+        _check(lib.stemseg_transpose_pad(_lib.ptr(dy), 0, t, h, w, co, pad, 1, _lib.ptr(dy_t), planes,
+                                         _lib.stream_ptr()))
+        _check(lib.stemseg_transpose_pad(_lib.ptr(x_planes.tensor), 1, t, h, w, ci, pad, shifts, _lib.ptr(x_t), planes,
+                                         _lib.stream_ptr()))
+        ks = lib.stemseg_wgrad_k_splits(co, ci, t, h, w, kernel_size, planes)
+        slices = _empty((ks, taps, co, ci), torch.float32, dev)
+        _check(lib.stemseg_conv3d_wgrad(_lib.ptr(dy_t), _lib.ptr(x_t), co, ci, t, h, w, kernel_size, planes, ks,
+                                        _lib.ptr(slices), _lib.stream_ptr()))
     _check(lib.stemseg_wgrad_reduce(_lib.ptr(slices), ks, co, taps, ci, _lib.ptr(dst), dst.shape[1], cin_begin, 0,
                                     _lib.stream_ptr()))
 
@@ -181,10 +196,11 @@ def training_backward(head, saved, grad_out):
         d_low = _empty((nn_, th // tscale[k], hh // 2, wh // 2, ch), torch.float32, dev)
         _check(lib.stemseg_upsample_transpose(_lib.ptr(d_high), nn_, th, hh, wh, ch, tscale[k], _lib.ptr(d_low),
                                               _lib.stream_ptr()))
-        branch_grad[k + 1] = D.conv3d(_to_planes(d_high, planes), dgrad_w[(merge, "skip")])       # W_b^T dz
-        _wgrad(d_high, m["f_in"], 1, planes, wflat, m["x_in"].c)
-        d_xin = D.conv3d(_to_planes(d_low, planes), dgrad_w[(merge, "up")])                        # W_a^T d y_low
-        _wgrad(d_low, m["x_in"], 1, planes, wflat, 0)
+        d_high_p, d_low_p = _to_planes(d_high, planes), _to_planes(d_low, planes)
+        branch_grad[k + 1] = D.conv3d(d_high_p, dgrad_w[(merge, "skip")])                           # W_b^T dz
+        _wgrad(d_high, d_high_p, m["f_in"], 1, planes, wflat, m["x_in"].c)
+        d_xin = D.conv3d(d_low_p, dgrad_w[(merge, "up")])                                           # W_a^T d y_low
+        _wgrad(d_low, d_low_p, m["x_in"], 1, planes, wflat, 0)
         grads[merge + ".weight"] = wgrad_dst
         d_high = d_xin
     branch_grad[0] = d_high
@@ -221,9 +237,10 @@ def training_backward(head, saved, grad_out):
                                            _lib.stream_ptr()))
             grads[bname] = d_bias
             wgrad_dst = torch.empty_like(params[wname])
-            _wgrad(dy, st["a_in"], 3, planes, wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 27), 0)
+            dy_p = _to_planes(dy, planes)
+            _wgrad(dy, dy_p, st["a_in"], 3, planes, wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 27), 0)
             grads[wname] = wgrad_dst
-            d = D.conv3d(_to_planes(dy, planes), dgrad_w[wname])     # dgrad: conv with flipped / transposed weights
+            d = D.conv3d(dy_p, dgrad_w[wname])                       # dgrad: conv with flipped / transposed weights
         feat_grads.append(d.permute(0, 4, 1, 2, 3))                  # NDHWC -> NCTHW view
     return feat_grads, grads
 

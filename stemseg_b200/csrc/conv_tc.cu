@@ -529,6 +529,233 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Direct weight gradient: dW[tap][co][ci] = sum_vox dy[vox][co] * x[vox + tap][ci] as a tcgen05 GEMM whose REDUCTION
+// dimension is the voxel index.  Both operands stay in the NDHWC bf16 plane layout of the forward pass and are fed to
+// the tensor core as MN-major tiles: one TMA box = (64 channels) x (32 voxels) lands as 32 rows of 128 bytes, which
+// is exactly the canonical SWIZZLE_128B MN-major atom sequence (8 K-rows x 64 MN-elements per 1024-byte atom; SBO =
+// 1024 bytes between 8-row groups, LBO = one box = 4096 bytes between 64-channel blocks).  The tap shift and the
+// zero padding are, as in the forward pass, TMA start coordinates + out-of-bounds zero fill on the x operand -- no
+// transposed copies, no padded volume, no im2col buffer.
+//   M = 128 output channels (two 64-channel boxes of dy), N = BLOCK_N input channels (BLOCK_N/64 boxes of x),
+//   K = 32 voxels per pipeline stage (two UMMA K=16 steps).
+// tile = (tap, m_tile, n_tile, k_split); taps vary fastest so that CTAs running at the same time read the same voxel
+// range (L2 reuse across the 27 taps).  Partial sums per k_split are reduced by stemseg_wgrad_reduce.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+    int t, h, w;
+    int cin, cout;
+    int ntaps;
+    int tt, th, tw;            // 32-voxel box
+    int tiles_t, tiles_h, tiles_w, k_tiles;
+    int m_tiles, n_tiles, k_splits;
+    int num_tiles;
+    int num_stages;
+    float* out;                // [k_splits][ntaps][cout][cin]
+};
+
+constexpr int kWgBoxVoxels = 32;
+constexpr int kWgBoxBytes = kWgBoxVoxels * 128;     // 64 channels x 32 voxels, bf16
+
+// MN-major SWIZZLE_128B operand: LBO = stride between 64-element blocks along M/N, SBO = stride between 8-row K groups
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t lbo = static_cast<uint64_t>(kWgBoxBytes) >> 4;
+    constexpr uint64_t sbo = 1024ull >> 4;
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BLOCK_N, int PLANES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap dy_map0, const __grid_constant__ CUtensorMap dy_map1,
+                  const __grid_constant__ CUtensorMap x_map0, const __grid_constant__ CUtensorMap x_map1,
+                  const WgradParams p) {
+    constexpr int NB = BLOCK_N / 64;
+    constexpr int A_BYTES = 2 * kWgBoxBytes;                // per plane: 128 output channels
+    constexpr int B_BYTES = NB * kWgBoxBytes;               // per plane: BLOCK_N input channels
+    constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    constexpr int TMEM_COLS = tmem_columns<BLOCK_N>();
+    static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "wgrad N tile is a multiple of 64 channels");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.num_stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    struct WTile { int tap, m_tile, n_tile, k_begin, k_end; };
+    auto decode = [&](int tile) -> WTile {
+        WTile c;
+        c.tap = tile % p.ntaps;
+        tile /= p.ntaps;
+        c.m_tile = tile % p.m_tiles;
+        tile /= p.m_tiles;
+        c.n_tile = tile % p.n_tiles;
+        const int ks = tile / p.n_tiles;
+        c.k_begin = static_cast<int>(static_cast<long long>(ks) * p.k_tiles / p.k_splits);
+        c.k_end = static_cast<int>(static_cast<long long>(ks + 1) * p.k_tiles / p.k_splits);
+        return c;
+    };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&dy_map0);
+        prefetch_tmap(&x_map0);
+        if (PLANES == 2) {
+            prefetch_tmap(&dy_map1);
+            prefetch_tmap(&x_map1);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            mbar_init(tmem_full_bar + a, 1);
+            mbar_init(tmem_empty_bar + a, kNumEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const WTile tc = decode(tile);
+                int dt = 0, dh = 0, dw = 0;
+                if (p.ntaps == 27) {
+                    dt = tc.tap / 9 - 1;
+                    dh = (tc.tap / 3) % 3 - 1;
+                    dw = tc.tap % 3 - 1;
+                }
+                for (int kt = tc.k_begin; kt < tc.k_end; ++kt) {
+                    const int w0 = (kt % p.tiles_w) * p.tw;
+                    const int h0 = ((kt / p.tiles_w) % p.tiles_h) * p.th;
+                    const int t0 = (kt / (p.tiles_w * p.tiles_h)) * p.tt;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* st = smem + stage * STAGE_BYTES;
+                    mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+#pragma unroll
+                    for (int pl = 0; pl < PLANES; ++pl) {
+                        const CUtensorMap* dm = pl == 0 ? &dy_map0 : &dy_map1;
+                        const CUtensorMap* xm = pl == 0 ? &x_map0 : &x_map1;
+#pragma unroll
+                        for (int mb = 0; mb < 2; ++mb)
+                            tma_load_5d(dm, full_bar + stage, st + (pl * 2 + mb) * kWgBoxBytes,
+                                        tc.m_tile * kBlockM + mb * 64, w0, h0, t0, 0);
+                        uint8_t* sb = st + PLANES * A_BYTES + pl * B_BYTES;
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+                            tma_load_5d(xm, full_bar + stage, sb + nb * kWgBoxBytes, tc.n_tile * BLOCK_N + nb * 64,
+                                        w0 + dw, h0 + dh, t0 + dt, 0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc<BLOCK_N>() | (1u << 15) | (1u << 16);     // A and B are MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const WTile tc = decode(tile);
+            mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+            const int num_k = tc.k_end - tc.k_begin;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(full_bar + stage, phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b0 = a0 + PLANES * A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < kWgBoxVoxels / kUmmaK; ++k) {
+                        const uint32_t koff = k * kUmmaK * 128;        // 16 voxel rows of 128 bytes
+                        const uint64_t a_hi = make_mnmajor_desc(a0 + koff);
+                        const uint64_t b_hi = make_mnmajor_desc(b0 + koff);
+                        umma_bf16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (PLANES == 2) {
+                            const uint64_t a_lo = make_mnmajor_desc(a0 + A_BYTES + koff);
+                            const uint64_t b_lo = make_mnmajor_desc(b0 + B_BYTES + koff);
+                            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar + stage);
+                    if (kb == num_k - 1) umma_commit(tmem_full_bar + acc);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue warps (2..5): fp32 partial sums -> [k_split][tap][co][ci] =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const WTile tc = decode(tile);
+            const int ks = tile / (p.ntaps * p.m_tiles * p.n_tiles);
+            const int co = tc.m_tile * kBlockM + row;
+            mbar_wait(tmem_full_bar + acc, acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BLOCK_N);
+            float* out_row = p.out + ((static_cast<size_t>(ks) * p.ntaps + tc.tap) * p.cout + co) * p.cin +
+                             static_cast<size_t>(tc.n_tile) * BLOCK_N;
+            const int cols_left = p.cin - tc.n_tile * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c, v);
+                tmem_ld_wait();
+                if (co < p.cout && c < cols_left) {          // cin is a multiple of 32: whole 32-column groups
+#pragma unroll
+                    for (int q = 0; q < 32; q += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[q + 0]);
+                        o.y = __uint_as_float(v[q + 1]);
+                        o.z = __uint_as_float(v[q + 2]);
+                        o.w = __uint_as_float(v[q + 3]);
+                        *reinterpret_cast<float4*>(out_row + c + q) = o;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tmem_empty_bar + acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -801,6 +1028,138 @@ extern "C" int32_t stemseg_conv1x1_head_output(const void* act_planes, const voi
     head.t_abs = time_scale;
     head.head_out = out;
     return conv3d_impl(act_planes, weight_planes, nullptr, nullptr, nullptr, s, max_ctas, stream_, &head);
+}
+
+namespace {
+// 32-voxel box (tt, th, tw) with the fewest tiles (ties: wider rows)
+void choose_box32(int t, int h, int w, int* tt, int* th, int* tw) {
+    long long best = -1;
+    for (int a = 1; a <= kWgBoxVoxels; a *= 2)
+        for (int b = 1; a * b <= kWgBoxVoxels; b *= 2) {
+            const int c = kWgBoxVoxels / (a * b);
+            const long long vol = 1ll * ((t + a - 1) / a) * ((h + b - 1) / b) * ((w + c - 1) / c);
+            const long long score = vol * 1024 - c * 8 - b;
+            if (best < 0 || score < best) {
+                best = score;
+                *tt = a; *th = b; *tw = c;
+            }
+        }
+}
+int wgrad_direct_block_n(int cin) { return cin % 256 == 0 ? 256 : cin % 128 == 0 ? 128 : 64; }
+
+int encode_box_map(CUtensorMap* map, const void* base, int channels, int t, int h, int w, int tt, int th, int tw) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return STEMSEG_ERR_CUDA;
+    }
+    const cuuint64_t dims[5] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                                static_cast<cuuint64_t>(t), 1};
+    const cuuint64_t c2 = static_cast<cuuint64_t>(channels) * 2;
+    const cuuint64_t strides[4] = {c2, c2 * w, c2 * w * h, c2 * w * h * t};
+    const cuuint32_t box[5] = {64u, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tt), 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(wgrad operand, %d channels) failed with CUresult %d", channels, static_cast<int>(r));
+        return STEMSEG_ERR_CUDA;
+    }
+    return STEMSEG_OK;
+}
+
+template <int BLOCK_N, int PLANES>
+int launch_wgrad(const CUtensorMap* maps, WgradParams& p, cudaStream_t stream) {
+    constexpr int stage = PLANES * (2 + BLOCK_N / 64) * kWgBoxBytes;
+    const int fixed = 1024 + 256;
+    int stages = (kSmemBudget) / stage;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages * stage + fixed > kSmemLimit) stages = (kSmemLimit - fixed) / stage;
+    if (stages < 2) {
+        set_error("conv_wgrad: stage of %d bytes does not fit shared memory", stage);
+        return STEMSEG_ERR_UNSUPPORTED;
+    }
+    p.num_stages = stages;
+    auto kernel = conv_wgrad_kernel<BLOCK_N, PLANES>;
+    SS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    int grid = device_sm_count();
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kernel<<<grid, kNumThreads, stages * stage + fixed, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+}  // namespace
+
+extern "C" int32_t stemseg_wgrad_direct_k_splits(int32_t cout, int32_t cin, int32_t t, int32_t h, int32_t w,
+                                                 int32_t kernel_size) {
+    if (cout < 1 || cin < 32 || t < 1 || h < 1 || w < 1) return 1;
+    int tt, th, tw;
+    choose_box32(t, h, w, &tt, &th, &tw);
+    const long long k_tiles = 1ll * ((t + tt - 1) / tt) * ((h + th - 1) / th) * ((w + tw - 1) / tw);
+    const int bn = wgrad_direct_block_n(cin);
+    const long long base = 1ll * (kernel_size == 3 ? 27 : 1) * ((cout + kBlockM - 1) / kBlockM) * ((cin + bn - 1) / bn);
+    long long k = (2ll * device_sm_count() + base - 1) / base;            // ~2 tiles per SM
+    if (k > k_tiles / 4) k = k_tiles / 4;                                 // at least 4 K blocks per tile
+    if (k > 64) k = 64;
+    if (k < 1) k = 1;
+    return static_cast<int32_t>(k);
+}
+
+// slices[ks][tap][co][ci] = sum over the voxel range of split ks of dy[vox][co] * x[vox + tap][ci]
+// dy_planes / x_planes: NDHWC bf16 planes [P][1][t][h][w][C] (stemseg_to_planes / the forward pass's activations)
+extern "C" int32_t stemseg_conv3d_wgrad_direct(const void* dy_planes, const void* x_planes, int32_t cout, int32_t cin,
+                                               int32_t t, int32_t h, int32_t w, int32_t kernel_size, int32_t planes,
+                                               int32_t k_splits, float* slices, void* stream_) {
+    SS_REQUIRE(dy_planes && x_planes && slices, "conv3d_wgrad_direct: null pointer");
+    SS_REQUIRE(planes == 1 || planes == 2, "conv3d_wgrad_direct: planes must be 1 or 2");
+    SS_REQUIRE(kernel_size == 3 || kernel_size == 1, "conv3d_wgrad_direct: kernel_size must be 1 or 3");
+    SS_REQUIRE(cout >= 8 && cout % 8 == 0 && cin >= 32 && cin % 32 == 0,
+               "conv3d_wgrad_direct: cout must be a multiple of 8 and cin of 32 (got %d, %d)", cout, cin);
+    SS_REQUIRE(t >= 1 && h >= 1 && w >= 1, "conv3d_wgrad_direct: empty volume");
+    SS_REQUIRE((reinterpret_cast<uintptr_t>(dy_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(slices) & 15) == 0,
+               "conv3d_wgrad_direct: pointers must be 16-byte aligned");
+    int rc = require_sm100();
+    if (rc != STEMSEG_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WgradParams p;
+    p.t = t; p.h = h; p.w = w;
+    p.cin = cin; p.cout = cout;
+    p.ntaps = kernel_size == 3 ? 27 : 1;
+    choose_box32(t, h, w, &p.tt, &p.th, &p.tw);
+    p.tiles_t = (t + p.tt - 1) / p.tt;
+    p.tiles_h = (h + p.th - 1) / p.th;
+    p.tiles_w = (w + p.tw - 1) / p.tw;
+    p.k_tiles = p.tiles_t * p.tiles_h * p.tiles_w;
+    const int bn = wgrad_direct_block_n(cin);
+    p.m_tiles = (cout + kBlockM - 1) / kBlockM;
+    p.n_tiles = (cin + bn - 1) / bn;
+    SS_REQUIRE(k_splits >= 1 && k_splits <= 64 && k_splits <= p.k_tiles,
+               "conv3d_wgrad_direct: k_splits %d out of range (1..min(64, %d))", k_splits, p.k_tiles);
+    p.k_splits = k_splits;
+    p.num_tiles = p.ntaps * p.m_tiles * p.n_tiles * p.k_splits;
+    p.num_stages = 0;
+    p.out = slices;
+    const size_t vox = static_cast<size_t>(t) * h * w;
+    CUtensorMap maps[4];
+    for (int pl = 0; pl < 2; ++pl) {
+        const int src = pl < planes ? pl : 0;
+        rc = encode_box_map(&maps[pl], static_cast<const uint8_t*>(dy_planes) + src * vox * cout * 2, cout, t, h, w, p.tt,
+                            p.th, p.tw);
+        if (rc != STEMSEG_OK) return rc;
+        rc = encode_box_map(&maps[2 + pl], static_cast<const uint8_t*>(x_planes) + src * vox * cin * 2, cin, t, h, w, p.tt,
+                            p.th, p.tw);
+        if (rc != STEMSEG_OK) return rc;
+    }
+    if (planes == 2) {
+        if (bn == 256) return launch_wgrad<256, 2>(maps, p, stream);
+        if (bn == 128) return launch_wgrad<128, 2>(maps, p, stream);
+        return launch_wgrad<64, 2>(maps, p, stream);
+    }
+    if (bn == 256) return launch_wgrad<256, 1>(maps, p, stream);
+    if (bn == 128) return launch_wgrad<128, 1>(maps, p, stream);
+    return launch_wgrad<64, 1>(maps, p, stream);
 }
 
 namespace {

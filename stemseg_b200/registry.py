@@ -79,3 +79,9 @@ def install_into_reference(replace_default=True):
         ref_main.SequentialClustering = SequentialClustering
     except Exception:        # the CLI module needs dataset dependencies that may be absent
         pass
+    # training: build_model() instantiates the name `EmbeddingLoss` imported into model_builder (model_builder.py:5,294)
+    from stemseg_b200.losses import EmbeddingLoss
+    import stemseg.modeling.losses as ref_losses
+    import stemseg.modeling.model_builder as ref_builder
+    ref_losses.EmbeddingLoss = EmbeddingLoss
+    ref_builder.EmbeddingLoss = EmbeddingLoss

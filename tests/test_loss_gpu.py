@@ -28,7 +28,7 @@ def _run_cuda(case, device, scale=1.0):
     out = case["out"].to(device).requires_grad_(True)
     od = {}
     total = crit(out, [{"masks": case["masks"].to(device), "ignore_masks": case["ignore"].to(device)}], od)
-    assert od[L.OUTPUT_OPTIMIZATION_LOSSES][L.LOSS_EMBEDDING] is total
+    assert float(od[L.OUTPUT_OPTIMIZATION_LOSSES][L.LOSS_EMBEDDING].detach()) == float(total.detach())
     (total * scale).backward()
     torch.cuda.synchronize()
     got = {"total": float(total), "lovasz": float(od[L.OUTPUT_OTHERS][L.LOSS_LOVASZ]),

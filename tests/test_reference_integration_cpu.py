@@ -36,6 +36,14 @@ def test_install_into_reference_and_strict_state_dict():
     import stemseg.inference.clusterers as ref_clusterers
     from stemseg_b200.clusterers import SequentialClustering
     assert ref_clusterers.SequentialClustering is SequentialClustering
+    import stemseg.modeling.model_builder as ref_builder
+    from stemseg_b200.losses import EmbeddingLoss
+    assert ref_builder.EmbeddingLoss is EmbeddingLoss
+    # constructed exactly as model_builder.py:294-298 does (upper-case cfg keys)
+    crit = ref_builder.EmbeddingLoss(min(cfg.MODEL.EMBEDDINGS.SCALE), embedding_size=cfg.MODEL.EMBEDDINGS.EMBEDDING_SIZE,
+                                     nbr_free_dims=len(cfg.TRAINING.LOSSES.EMBEDDING.FREE_DIM_STDS),
+                                     **cfg.TRAINING.LOSSES.EMBEDDING.d())
+    assert crit.num_input_channels == 2 * cfg.MODEL.EMBEDDINGS.EMBEDDING_SIZE - crit.n_free_dims + 1
 
 
 def test_same_seed_gives_identical_init():

@@ -80,7 +80,7 @@ def test_trainer_step_matches_oracles(cuda_device):
                      do.seediness_head(s64, f64, t, relu_masks=_cuda_relu_masks(saved[1]))), dim=1)
     ref = lo.loss_from_head_output(out, case["masks"], case["ignore"], 4, 2, [0.3, 0.3], **lc.WEIGHTS)
     ref["total"].backward()
-    got_total = float(output["optimization_losses"]["embedding_loss"])
+    got_total = float(output["optimization_losses"]["embedding_loss"].detach())
     assert abs(got_total - float(ref["total"])) <= 1e-4 * abs(float(ref["total"]))
     for fd, fr in zip(fdev, f64):
         assert float((fd.grad.double().cpu() - fr.grad).norm() / fr.grad.norm()) <= 2e-3
