@@ -38,8 +38,10 @@ def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
-def training_forward(head, feats):
-    """Eager forward keeping what the backward needs.  Returns (out, saved)."""
+def training_forward(head, feats, in_planes=None):
+    """Eager forward keeping what the backward needs.  Returns (out, saved).
+
+    in_planes: the four feature maps already packed (D.pack_activation), e.g. static buffers shared by several heads."""
     spec = head.head_spec()
     weights, out_spec = spec.weights, spec.out_spec
     planes = D.PRECISION_PLANES[head.precision]
@@ -48,10 +50,15 @@ def training_forward(head, feats):
     saved = {"blocks": {}, "merges": [], "planes": planes, "tscale": tscale}
     D.KEEP = []
     branch = []
-    for (name, n_stages), feat in zip(D.BLOCKS, feats):
-        if feat.shape[0] != 1:
-            raise NotImplementedError("training through the B200 heads handles one sub-clip per call (batch 1)")
-        a = D.pack_activation(feat, planes)
+    for b, (name, n_stages) in enumerate(D.BLOCKS):
+        if in_planes is not None:
+            a = in_planes[b]
+            if a.n != 1:
+                raise NotImplementedError("training through the B200 heads handles one sub-clip per call (batch 1)")
+        else:
+            if feats[b].shape[0] != 1:
+                raise NotImplementedError("training through the B200 heads handles one sub-clip per call (batch 1)")
+            a = D.pack_activation(feats[b], planes)
         stages = []
         for j in range(n_stages):
             conv, gamma, beta = weights.stages[name][j]
@@ -158,8 +165,20 @@ def _wgrad(dy, dy_planes, x_planes, kernel_size, planes, dst, cin_begin):
                                     _lib.stream_ptr()))
 
 
-def training_backward(head, saved, grad_out):
-    """-> (list of 4 feature gradients [1,C,T,h,w], {parameter name: gradient})."""
+def _dst(grad_dst, name, params):
+    if grad_dst is not None:
+        out = grad_dst[name]
+        if not out.is_contiguous() or out.shape != params[name].shape:
+            raise ValueError("gradient slot of %s must be a contiguous tensor of the parameter's shape" % name)
+        return out
+    return torch.empty_like(params[name])
+
+
+def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=True):
+    """-> (list of 4 feature gradients [1,C,T,h,w] (None when not needed), {parameter name: gradient}).
+
+    grad_dst: optional {parameter name: tensor of the parameter's shape}; gradients are WRITTEN there (e.g. views
+    into a flat all-reduce buffer) instead of into fresh tensors."""
     lib = _lib.load()
     planes, tscale = saved["planes"], saved["tscale"]
     spec = saved["out_spec"]
@@ -190,7 +209,7 @@ def training_backward(head, saved, grad_out):
     for k in (2, 1, 0):
         m = saved["merges"][k]
         merge = D.MERGES[k]
-        wgrad_dst = torch.empty_like(params[merge + ".weight"])
+        wgrad_dst = _dst(grad_dst, merge + ".weight", params)
         wflat = wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 1)
         nn_, th, hh, wh, ch = d_high.shape
         d_low = _empty((nn_, th // tscale[k], hh // 2, wh // 2, ch), torch.float32, dev)
@@ -236,12 +255,20 @@ def training_backward(head, saved, grad_out):
             _check(lib.stemseg_channel_sum(_lib.ptr(dy), t_ * h_ * w_, c_, _lib.ptr(d_bias), _lib.ptr(wsc), wsb,
                                            _lib.stream_ptr()))
             grads[bname] = d_bias
-            wgrad_dst = torch.empty_like(params[wname])
+            wgrad_dst = _dst(grad_dst, wname, params)
             dy_p = _to_planes(dy, planes)
             _wgrad(dy, dy_p, st["a_in"], 3, planes, wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 27), 0)
             grads[wname] = wgrad_dst
-            d = D.conv3d(dy_p, dgrad_w[wname])                       # dgrad: conv with flipped / transposed weights
-        feat_grads.append(d.permute(0, 4, 1, 2, 3))                  # NDHWC -> NCTHW view
+            if j == 0 and not need_feature_grads:                    # frozen backbone: skip the largest dgrad
+                d = None
+            else:
+                d = D.conv3d(dy_p, dgrad_w[wname])                   # dgrad: conv with flipped / transposed weights
+        feat_grads.append(None if d is None else d.permute(0, 4, 1, 2, 3))      # NDHWC -> NCTHW view
+    if grad_dst is not None:                                         # small gradients: copy into their slots
+        for name, gr in grads.items():
+            if gr.data_ptr() != grad_dst[name].data_ptr():
+                grad_dst[name].copy_(gr.reshape(grad_dst[name].shape))
+            grads[name] = grad_dst[name]
     return feat_grads, grads
 
 
@@ -261,7 +288,8 @@ class HeadFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         with torch.no_grad():
-            feat_grads, pgrads = training_backward(ctx.head, ctx.saved_state, grad_out)
+            feat_grads, pgrads = training_backward(ctx.head, ctx.saved_state, grad_out,
+                                                   need_feature_grads=any(ctx.feat_needs))
         ctx.saved_state = None
         outs = [None, None]
         outs += [fg if need else None for fg, need in zip(feat_grads, ctx.feat_needs)]

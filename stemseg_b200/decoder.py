@@ -225,8 +225,11 @@ class OutputSpec(object):
         dev = weight.device
         self.weight = weight.detach().to(torch.float32).contiguous()
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        self.activation = torch.tensor(list(activation), dtype=torch.int32, device=dev)
-        self.coordinate = torch.tensor(list(coordinate), dtype=torch.int32, device=dev)
+        # code tables may arrive as cached device tensors (no host->device copy: safe under CUDA-graph capture)
+        self.activation = activation if torch.is_tensor(activation) else \
+            torch.tensor(list(activation), dtype=torch.int32, device=dev)
+        self.coordinate = coordinate if torch.is_tensor(coordinate) else \
+            torch.tensor(list(coordinate), dtype=torch.int32, device=dev)
         self.n_out = int(self.weight.shape[0])
         self.time_scale = float(time_scale)
 

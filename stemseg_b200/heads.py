@@ -111,6 +111,16 @@ class _SqueezeExpandTrunk(nn.Module):
             self._head_set = None
         return self._packed
 
+    def _code_tables(self, activation, coordinate, device):
+        """Device copies of the per-output activation / coordinate codes, uploaded once per device."""
+        key = (tuple(activation), tuple(coordinate), str(device))
+        cache = getattr(self, "_codes_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, torch.tensor(list(activation), dtype=torch.int32, device=device),
+                     torch.tensor(list(coordinate), dtype=torch.int32, device=device))
+            self._codes_cache = cache
+        return cache[1], cache[2]
+
     def invalidate_packed_weights(self):
         """Call after modifying parameters behind autograd's back (e.g. the fused optimiser kernel writes the flat
         buffer the parameters are views of): the next forward / backward repacks the kernel-layout weights."""
@@ -165,8 +175,18 @@ class EmbeddingHead(_SqueezeExpandTrunk):
         self.tanh_activation = tanh_activation
         self.register_buffer("time_scale", torch.tensor(1.0, dtype=torch.float32))
 
+    def _time_scale_value(self):
+        """Host copy of the `time_scale` buffer, refreshed only when the buffer is modified (no sync per forward,
+        and none under CUDA-graph capture)."""
+        ver = (self.time_scale.data_ptr(), self.time_scale._version)
+        cache = getattr(self, "_time_scale_cache", None)
+        if cache is None or cache[0] != ver:
+            cache = (ver, float(self.time_scale))
+            self._time_scale_cache = cache
+        return cache[1]
+
     def _cache_key(self):
-        return super()._cache_key() + (float(self.time_scale),)
+        return super()._cache_key() + (self.time_scale.data_ptr(), self.time_scale._version)
 
     def _output_spec(self, state):
         e_out = self.conv_embedding.weight.shape[0]
@@ -183,8 +203,9 @@ class EmbeddingHead(_SqueezeExpandTrunk):
             bias.append(torch.zeros(1, device=ws[0].device))
             act.append(D.ACT_SIGMOID)
             coord.append(D.COORD_NONE)
-        return D.OutputSpec(torch.cat([w.detach() for w in ws], 0), torch.cat([b.detach() for b in bias], 0), act,
-                            coord, float(self.time_scale))
+        act_t, coord_t = self._code_tables(act, coord, ws[0].device)
+        return D.OutputSpec(torch.cat([w.detach() for w in ws], 0), torch.cat([b.detach() for b in bias], 0), act_t,
+                            coord_t, self._time_scale_value())
 
     def _scatter_output_grads(self, d_weight, d_bias, grads):
         e_out, v = self.conv_embedding.weight.shape[0], self.variance_channels
@@ -212,7 +233,8 @@ class SeedinessHead(_SqueezeExpandTrunk):
         self.conv_out = nn.Conv3d(self.inter_channels[3], 1, kernel_size=1, padding=0, bias=False)
 
     def _output_spec(self, state):
-        return D.OutputSpec(self.conv_out.weight.reshape(1, -1), None, [D.ACT_SIGMOID], [D.COORD_NONE])
+        act_t, coord_t = self._code_tables([D.ACT_SIGMOID], [D.COORD_NONE], self.conv_out.weight.device)
+        return D.OutputSpec(self.conv_out.weight.reshape(1, -1), None, act_t, coord_t)
 
     def _scatter_output_grads(self, d_weight, d_bias, grads):
         grads["conv_out.weight"] = d_weight.reshape(self.conv_out.weight.shape)
@@ -240,7 +262,8 @@ class SemsegHead(_SqueezeExpandTrunk):
 
     def _output_spec(self, state):
         j = self.conv_out.weight.shape[0]
-        return D.OutputSpec(self.conv_out.weight.reshape(j, -1), None, [D.ACT_IDENTITY] * j, [D.COORD_NONE] * j)
+        act_t, coord_t = self._code_tables([D.ACT_IDENTITY] * j, [D.COORD_NONE] * j, self.conv_out.weight.device)
+        return D.OutputSpec(self.conv_out.weight.reshape(j, -1), None, act_t, coord_t)
 
     def _scatter_output_grads(self, d_weight, d_bias, grads):
         grads["conv_out.weight"] = d_weight.reshape(self.conv_out.weight.shape)

@@ -48,40 +48,47 @@ def _kernel_count(voxels, n_instances):
     return count
 
 
+def embedding_loss_and_gradient(embedding_map, masks, ignore, crit):
+    """One C call: (losses [4] = total, lovasz, variance_smoothness, seediness; d total / d embedding_map).
+
+    embedding_map [1, E+V+1, T, H, W] fp32 CUDA, contiguous; masks [I,T,H,W] / ignore [T,H,W] uint8 CUDA (or None)."""
+    lib = _lib.load()
+    e, v = crit.embedding_size, crit.embedding_size - crit.n_free_dims
+    x = embedding_map
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError("EmbeddingLoss needs an fp32 CUDA embedding map (got %s on %s); there is no CPU path" % (
+            x.dtype, x.device))
+    x = x.contiguous()
+    voxels = x.shape[2] * x.shape[3] * x.shape[4]
+    n_inst = int(masks.shape[0])
+    if n_inst > _lib.STEMSEG_MAX_LOSS_INSTANCES:
+        raise ValueError("at most %d instances per sequence (got %d)" % (_lib.STEMSEG_MAX_LOSS_INSTANCES, n_inst))
+    dev = x.device
+    with torch.cuda.device(dev):
+        m = masks.to(device=dev, dtype=torch.uint8).contiguous()
+        ig = None if ignore is None else ignore.to(device=dev, dtype=torch.uint8).contiguous()
+        grad = torch.empty_like(x)
+        losses = torch.empty(4, dtype=torch.float32, device=dev)
+        ws_bytes = lib.stemseg_embedding_loss_workspace_bytes(voxels, n_inst)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stds = (ctypes.c_float * max(1, crit.n_free_dims))(*[float(s) for s in crit.free_dim_stds])
+        base = x.data_ptr()
+        seed_off = 4 * (e + v) * voxels
+        _lib.check(lib.stemseg_embedding_loss(
+            _lib.c_void_p(base), _lib.c_void_p(base + seed_off), _lib.ptr(m), _lib.ptr(ig), voxels, n_inst, e,
+            crit.n_free_dims, stds, crit.w_lovasz, crit.w_variance_smoothness, crit.w_seediness, crit.w,
+            _lib.ptr(losses), _lib.c_void_p(grad.data_ptr()), _lib.c_void_p(grad.data_ptr() + seed_off),
+            _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        _lib.KERNEL_LAUNCHES[0] += _kernel_count(voxels, n_inst)
+    return losses, grad
+
+
 class _EmbeddingLossFunction(torch.autograd.Function):
     """(embedding_map [1,C,T,H,W]) -> losses [4]; the gradient was computed together with the loss."""
 
     @staticmethod
     def forward(ctx, embedding_map, masks, ignore, crit):
-        lib = _lib.load()
-        e, v = crit.embedding_size, crit.embedding_size - crit.n_free_dims
-        x = embedding_map.detach()
-        if x.dtype != torch.float32 or not x.is_cuda:
-            raise ValueError("EmbeddingLoss needs an fp32 CUDA embedding map (got %s on %s); there is no CPU path" % (
-                x.dtype, x.device))
-        x = x.contiguous()
-        voxels = x.shape[2] * x.shape[3] * x.shape[4]
-        n_inst = int(masks.shape[0])
-        if n_inst > _lib.STEMSEG_MAX_LOSS_INSTANCES:
-            raise ValueError("at most %d instances per sequence (got %d)" % (_lib.STEMSEG_MAX_LOSS_INSTANCES, n_inst))
-        dev = x.device
-        with torch.cuda.device(dev):
-            m = masks.to(device=dev, dtype=torch.uint8).contiguous()
-            ig = None if ignore is None else ignore.to(device=dev, dtype=torch.uint8).contiguous()
-            grad = torch.empty_like(x)
-            losses = torch.empty(4, dtype=torch.float32, device=dev)
-            ws_bytes = lib.stemseg_embedding_loss_workspace_bytes(voxels, n_inst)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            stds = (ctypes.c_float * max(1, crit.n_free_dims))(*[float(s) for s in crit.free_dim_stds])
-            base = x.data_ptr()
-            seed_off = 4 * (e + v) * voxels
-            _lib.check(lib.stemseg_embedding_loss(
-                _lib.c_void_p(base), _lib.c_void_p(base + seed_off), _lib.ptr(m), _lib.ptr(ig), voxels, n_inst, e,
-                crit.n_free_dims, stds, crit.w_lovasz, crit.w_variance_smoothness, crit.w_seediness, crit.w,
-                _lib.ptr(losses), _lib.c_void_p(grad.data_ptr()), _lib.c_void_p(grad.data_ptr() + seed_off),
-                _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
-            _lib.KERNEL_LAUNCHES[0] += _kernel_count(voxels, n_inst)
-        ctx.grad = grad
+        losses, ctx.grad = embedding_loss_and_gradient(embedding_map.detach(), masks, ignore, crit)
         return losses
 
     @staticmethod

@@ -12,6 +12,15 @@ same step for the heads' parameters is laid out for one process per B200:
     of the head that autograd runs next (``GradientExchange``; gloo in the CPU tests);
   * the mean over ranks is folded into the SGD pass (grad_scale = 1 / world_size).
 
+Two execution modes of ``DecoderTrainer.step``:
+  * ``use_graph=False``: through torch autograd (``loss.backward()``), i.e. exactly what the reference's training loop
+    drives when the B200 heads / loss are installed into it -- ~500 kernel launches per step issued from Python;
+  * ``use_graph=True`` (default on CUDA): the same kernels issued WITHOUT the autograd engine (forward, loss+gradient,
+    backward of each head, optimiser) and captured once per input shape into three CUDA graphs -- [weights repack +
+    forward of all heads + loss + backward of the last head] / [backward of the first head + feature-gradient sum] /
+    [fused SGD] -- so a step is 4 pack launches + 3 graph replays, with the per-head NCCL all-reduce issued between
+    the replays (the first reduction overlaps the second graph).
+
 Forward/backward of the heads: stemseg_b200.autograd (tcgen05 conv / dgrad / wgrad kernels); loss + its gradient:
 stemseg_b200.losses.EmbeddingLoss (csrc/embedding_loss.cu).  torch supplies autograd bookkeeping, streams, NCCL.
 The torch ResNet-101 backbone is out of scope (SURVEY.md §8): its parameters, if trained, stay with torch's optimiser;
@@ -122,7 +131,12 @@ class DecoderTrainer(object):
     heads: dict with 'embedding' (EmbeddingHead) and optionally 'seediness' (SeedinessHead), already on the device.
     criterion: stemseg_b200.losses.EmbeddingLoss.  Hyper-parameters default to defaults.yaml:17-31."""
 
-    def __init__(self, heads, criterion, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True, group=None):
+    def __init__(self, heads, criterion, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True, group=None,
+                 use_graph=True, need_feature_grads=True):
+        self.use_graph = use_graph
+        self.need_feature_grads = need_feature_grads
+        self.group = group
+        self._graphs = {}
         self.embedding_head = heads["embedding"]
         self.seediness_head = heads.get("seediness")
         self.criterion = criterion
@@ -146,7 +160,10 @@ class DecoderTrainer(object):
         return loss, output
 
     def step(self, feats_32_16_8_4, targets):
-        """One optimisation step; returns the loss dict (device scalars, no host synchronisation)."""
+        """One optimisation step; returns the loss dict (device scalars, no host synchronisation).  In graph mode the
+        dict also carries 'feature_grads' (4 tensors [1,C,T,h,w], d loss / d feature map, valid until the next step)."""
+        if self.use_graph:
+            return self._step_graph(feats_32_16_8_4, targets)
         for flat in self.flats:
             flat.zero_grad()
         loss, output = self.forward_loss(feats_32_16_8_4, targets)
@@ -156,3 +173,120 @@ class DecoderTrainer(object):
             sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
             mod.invalidate_packed_weights()          # the kernel wrote the parameters behind autograd's back
         return output
+
+    # ---- graph mode ---------------------------------------------------------------------------------------------
+    def _modules(self):
+        return [self.embedding_head] + ([self.seediness_head] if self.seediness_head is not None else [])
+
+    def _grad_slots(self, flat):
+        names = {id(p): n for n, p in flat.module.named_parameters()}
+        return {names[id(p)]: flat.grad[off:off + p.numel()].view_as(p) for p, off in zip(flat.params, flat.offsets)}
+
+    def _segments(self, entry):
+        """The three captured segments as closures over the static buffers of `entry`."""
+        from stemseg_b200 import autograd as A
+        from stemseg_b200.losses import embedding_loss_and_gradient
+        mods, flats = self._modules(), self.flats
+        state = {}
+
+        def seg_forward_loss_backward_last():
+            saved, outs = [], []
+            for m in mods:
+                m.invalidate_packed_weights()                 # the repack kernels become part of the graph
+                out, sv = A.training_forward(m, None, in_planes=entry["in_planes"])
+                outs.append(out)
+                saved.append(sv)
+            emb_map = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)      # model_builder.py:198-201
+            losses, grad = embedding_loss_and_gradient(emb_map, entry["masks"], entry["ignore"], self.criterion)
+            entry["losses"] = losses
+            c0 = outs[0].shape[1]
+            state["grads_out"] = [grad[:, :c0]] + ([grad[:, c0:]] if len(outs) > 1 else [])
+            state["saved"] = saved
+            last = len(mods) - 1
+            fg, _ = A.training_backward(mods[last], saved[last], state["grads_out"][last],
+                                        grad_dst=self._grad_slots(flats[last]),
+                                        need_feature_grads=self.need_feature_grads)
+            state["fg_last"] = fg
+
+        def seg_backward_first():
+            fg = state["fg_last"]
+            if len(mods) > 1:
+                fg0, _ = A.training_backward(mods[0], state["saved"][0], state["grads_out"][0],
+                                             grad_dst=self._grad_slots(flats[0]),
+                                             need_feature_grads=self.need_feature_grads)
+                if self.need_feature_grads:                   # both heads read the same pyramid
+                    fg = [a + b for a, b in zip(fg0, fg)]
+            entry["feature_grads"] = fg if self.need_feature_grads else None
+
+        def seg_optimizer():
+            for flat in flats:
+                sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
+
+        return [seg_forward_loss_backward_last, seg_backward_first, seg_optimizer]
+
+    def _capture(self, feats, targets):
+        from stemseg_b200 import decoder as D
+        dev = feats[0].device
+        planes = D.PRECISION_PLANES[self.embedding_head.precision]
+        masks = targets[0]["masks"]
+        entry = {"in_planes": [D.pack_activation(f.detach(), planes) for f in feats],
+                 "masks": masks.to(device=dev, dtype=torch.uint8).contiguous().clone(),
+                 "ignore": targets[0]["ignore_masks"].to(device=dev, dtype=torch.uint8).contiguous().clone()}
+        segments = self._segments(entry)
+        # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, allocator) -- without the optimiser
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            segments[0]()
+            segments[1]()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graphs, pool = [], None
+        for seg in segments:
+            g = torch.cuda.CUDAGraph()
+            before = _lib.KERNEL_LAUNCHES[0]
+            with torch.cuda.graph(g, pool=pool):
+                seg()
+            pool = g.pool()
+            graphs.append((g, _lib.KERNEL_LAUNCHES[0] - before))
+        entry["graphs"] = graphs
+        entry["segments"] = segments           # keeps every captured buffer alive
+        for flat in self.flats:                # the captures ran nothing: gradients / momentum are still untouched
+            flat.grad.zero_()
+        return entry
+
+    def _step_graph(self, feats, targets):
+        from stemseg_b200 import decoder as D
+        if len(targets) != 1 or feats[0].shape[0] != 1:
+            raise NotImplementedError("one sub-clip per rank per step (the reference's MAX_SAMPLES_PER_GPU = 1)")
+        masks, ignore = targets[0]["masks"], targets[0]["ignore_masks"]
+        key = (tuple(tuple(f.shape) for f in feats), tuple(masks.shape), str(feats[0].device))
+        dev = feats[0].device
+        with torch.no_grad(), torch.cuda.device(dev):
+            entry = self._graphs.get(key)
+            if entry is None:
+                entry = self._capture(feats, targets)
+                self._graphs[key] = entry
+            planes = D.PRECISION_PLANES[self.embedding_head.precision]
+            for f, pl in zip(feats, entry["in_planes"]):
+                D.pack_activation(f.detach(), planes, out=pl)
+            entry["masks"].copy_(masks, non_blocking=True)
+            entry["ignore"].copy_(ignore, non_blocking=True)
+            pending = []
+            (g1, k1), (g2, k2), (g3, k3) = entry["graphs"]
+            g1.replay()
+            if self.world > 1:                 # gradients of the last head are complete: reduce while g2 runs
+                pending.append(dist.all_reduce(self.flats[-1].grad, group=self.group, async_op=True))
+            g2.replay()
+            if self.world > 1 and len(self.flats) > 1:
+                pending.append(dist.all_reduce(self.flats[0].grad, group=self.group, async_op=True))
+            for work in pending:
+                work.wait()
+            g3.replay()
+            _lib.KERNEL_LAUNCHES[0] += k1 + k2 + k3
+            for m in self._modules():
+                m.invalidate_packed_weights()  # the packed copies inside the graph pool predate this step's update
+        losses = entry["losses"]
+        return {"optimization_losses": {"embedding_loss": losses[0]},
+                "others": {"lovasz_loss": losses[1], "variance_smoothness_loss": losses[2], "seediness_loss": losses[3]},
+                "feature_grads": entry["feature_grads"]}

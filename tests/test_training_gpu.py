@@ -47,7 +47,8 @@ def _small_heads(device):
     return emb, seed, emb_sd, seed_sd
 
 
-def test_trainer_step_matches_oracles(cuda_device):
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_step_matches_oracles(use_graph, cuda_device):
     from stemseg_b200 import autograd as A
     from stemseg_b200.losses import EmbeddingLoss
     from stemseg_b200.training import DecoderTrainer
@@ -58,7 +59,8 @@ def test_trainer_step_matches_oracles(cuda_device):
     crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3], weight_variance_smoothness=10.0,
                          weight_lovasz=1.0, weight_regularization=0.001, weight_seediness=1.0, weight=1.0)
     lr, mom, wd = 0.1, 0.9, 1e-4
-    trainer = DecoderTrainer({"embedding": emb, "seediness": seed}, crit, lr=lr, momentum=mom, weight_decay=wd)
+    trainer = DecoderTrainer({"embedding": emb, "seediness": seed}, crit, lr=lr, momentum=mom, weight_decay=wd,
+                             use_graph=use_graph)
     before = {("e", k): v.detach().cpu().double().clone() for k, v in emb.named_parameters()}
     before.update({("s", k): v.detach().cpu().double().clone() for k, v in seed.named_parameters()})
     fdev = [f.to(cuda_device).requires_grad_(True) for f in feats]
@@ -66,11 +68,14 @@ def test_trainer_step_matches_oracles(cuda_device):
     A.DEBUG_SAVED = []
     try:
         output = trainer.step(fdev, targets)
-        saved = list(A.DEBUG_SAVED)
+        # graph mode runs the forward three times (warm-up, capture, replay); the captured buffers (the last two
+        # entries) hold the values of the replay
+        saved = list(A.DEBUG_SAVED)[-2:]
     finally:
         A.DEBUG_SAVED = None
     torch.cuda.synchronize()
     assert len(saved) == 2
+    feat_grads = output["feature_grads"] if use_graph else [f.grad for f in fdev]
 
     # float64 oracle of the same step, differentiated along the CUDA forward's ReLU pattern
     e64 = {k: (v.double().clone().requires_grad_(True) if v.dim() > 0 else v) for k, v in emb_sd.items()}
@@ -82,8 +87,9 @@ def test_trainer_step_matches_oracles(cuda_device):
     ref["total"].backward()
     got_total = float(output["optimization_losses"]["embedding_loss"].detach())
     assert abs(got_total - float(ref["total"])) <= 1e-4 * abs(float(ref["total"]))
-    for fd, fr in zip(fdev, f64):
-        assert float((fd.grad.double().cpu() - fr.grad).norm() / fr.grad.norm()) <= 2e-3
+    for fg, fr in zip(feat_grads, f64):
+        assert tuple(fg.shape) == tuple(fr.shape)
+        assert float((fg.double().cpu() - fr.grad).norm() / fr.grad.norm()) <= 2e-3
 
     worst = 0.0
     for tag, mod, sd64 in (("e", emb, e64), ("s", seed, s64)):
@@ -110,3 +116,33 @@ def test_trainer_step_matches_oracles(cuda_device):
     stale = do.embedding_head(emb_sd, feats, t, 4, "xyff", True, False)
     assert float((got - want).abs().max() / want.abs().max()) <= 1e-4
     assert float((stale - want).abs().max()) > 10 * float((got - want).abs().max())
+
+
+def test_graph_steps_track_the_autograd_steps(cuda_device):
+    """Three consecutive steps: the CUDA-graph trainer and the autograd trainer follow the same parameter trajectory
+    (same kernels, different launch mechanism), including the momentum state and the per-step weight repack."""
+    from stemseg_b200.losses import EmbeddingLoss
+    from stemseg_b200.training import DecoderTrainer
+    t, h4, w4 = 4, 24, 32
+    feats = do.seeded_features(603, 1, 32, t, h4, w4)
+    case = lo.seeded_case(seed=604, t=t, h=h4, w=w4, embedding_size=4, n_free=2, instances=2)
+    results = []
+    for use_graph in (False, True):
+        emb, seed, _, _ = _small_heads(cuda_device)
+        crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3],
+                             weight_variance_smoothness=10.0, weight_lovasz=1.0, weight_regularization=0.001,
+                             weight_seediness=1.0, weight=1.0)
+        trainer = DecoderTrainer({"embedding": emb, "seediness": seed}, crit, lr=0.05, use_graph=use_graph)
+        targets = [{"masks": case["masks"].to(cuda_device), "ignore_masks": case["ignore"].to(cuda_device)}]
+        losses = []
+        for step in range(3):
+            fdev = [(f * (1.0 + 0.1 * step)).to(cuda_device).requires_grad_(True) for f in feats]
+            out = trainer.step(fdev, targets)
+            losses.append(float(out["optimization_losses"]["embedding_loss"].detach()))
+        torch.cuda.synchronize()
+        results.append((losses, torch.cat([f.data.clone() for f in trainer.flats]).cpu()))
+    (l_a, p_a), (l_g, p_g) = results
+    assert l_a[0] != l_a[2]
+    for a, g in zip(l_a, l_g):
+        assert abs(a - g) <= 1e-5 * abs(a)
+    assert float((p_a - p_g).norm() / p_a.norm()) <= 1e-6
