@@ -747,40 +747,17 @@ def run_train(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
 
-    # phase breakdown (rank 0, informational): forward / loss / backward / exchange+SGD, CUDA events
+    # the same step driven through torch autograd (what the reference's training loop does with the B200 heads and
+    # loss installed): ~500 launches issued from Python instead of 3 graph replays.  Single-GPU runs only (the
+    # autograd path issues its own collectives).
     phases = {}
-    if rank == 0:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        for flat in trainer.flats:
-            flat.zero_grad()
-        for f in dev_feats:
-            f.grad = None
-        torch.cuda.synchronize()
-        ev[0].record()
-        out = torch.cat((emb(dev_feats), seedh(dev_feats)), dim=1)
-        ev[1].record()
-        od = {}
-        loss = crit(out, targets, od)
-        ev[2].record()
-        loss.backward()
-        ev[3].record()
-        trainer.exchange.finish()
-        from stemseg_b200.training import sgd_step
-        for flat, mod in zip(trainer.flats, (emb, seedh)):
-            sgd_step(flat, trainer.lr, trainer.momentum, trainer.weight_decay, trainer.nesterov, 1.0 / world)
-            mod.invalidate_packed_weights()
-        ev[4].record()
-        torch.cuda.synchronize()
-        for name, i in (("forward_ms", 0), ("loss_ms", 1), ("backward_ms", 2), ("exchange_sgd_ms", 3)):
-            phases[name] = ev[i].elapsed_time(ev[i + 1])
-        # per-launch conv timing of one eager step (forward, dgrad and wgrad all go through conv_tc_kernel)
-        decoder.PROFILE_EVENTS = []
-        step_resident()
-        torch.cuda.synchronize()
-        conv_ms = sum(a.elapsed_time(b) for _, a, b in decoder.PROFILE_EVENTS)
-        phases["conv_launches"] = len(decoder.PROFILE_EVENTS)
-        phases["conv_ms"] = conv_ms
-        decoder.PROFILE_EVENTS = None
+    if world == 1:
+        trainer.use_graph = False
+        for _ in range(2):
+            step_resident()
+        phases["autograd_mode_ms_per_step"] = timed(step_resident, 3) / 3
+        trainer.use_graph = True
+        phases["graph_mode_ms_per_step"] = ms_total / args.steps
     if world > 1:
         dist.barrier()
     if rank != 0:

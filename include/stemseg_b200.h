@@ -296,6 +296,20 @@ int32_t stemseg_head_backward(const float* z, const float* y_low, int32_t n, int
                               int32_t t_scale, const float* out_weight, const float* out_bias,
                               const int32_t* activation, int32_t n_out, const float* grad_out, float* dx,
                               float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+/* Training-path output heads over the merged feature x = z + up(y_low) kept in fp32 (csrc/head_train.cu):
+ * stemseg_upsample_add_f32 forms x in place of z once per step; stemseg_head_output_x / stemseg_head_backward_x are the
+ * streaming forward / backward of the 1x1x1 output convs + activations + coordinate offsets
+ * (embedding_decoder.py:90-96,131-145; seediness_decoder.py:80,112; semseg_decoder.py:86-87,116). */
+int32_t stemseg_upsample_add_f32(float* z, const float* y_low, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                                 int32_t t_scale, void* stream);
+int32_t stemseg_head_output_x(const float* x, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                              const float* out_weight, const float* out_bias, const int32_t* activation,
+                              const int32_t* coordinate, int32_t n_out, float time_scale, float* out, void* stream);
+size_t stemseg_head_backward_x_workspace_bytes(int32_t c);
+int32_t stemseg_head_backward_x(const float* x, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
+                                const float* out_weight, const float* out_bias, const int32_t* activation, int32_t n_out,
+                                const float* grad_out, float* dx, float* d_weight, float* d_bias, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* adjoint of the trilinear (t_scale, 2, 2) up-sampling: d_low [n][t/t_scale][h/2][w/2][c] from d_high [n][t][h][w][c] */
 int32_t stemseg_upsample_transpose(const float* d_high, int32_t n, int32_t t, int32_t h, int32_t w, int32_t c,
                                    int32_t t_scale, float* d_low, void* stream);

@@ -78,11 +78,17 @@ def training_forward(head, feats, in_planes=None):
         w_up, w_skip = weights.merges[k]
         y_low = D.conv3d(x, w_up)
         z = D.conv3d(branch[k + 1], w_skip)
-        saved["merges"].append({"x_in": x, "f_in": branch[k + 1], "y_low": y_low, "z": z})
+        saved["merges"].append({"x_in": x, "f_in": branch[k + 1]})
         if k < 2:
             x = D.upsample_add(z, y_low, tscale[k], planes)
         else:
-            out = D.head_output(z, y_low, tscale[k], out_spec)
+            # the merged feature x4 = z + up(y_low) is formed once, in fp32, in place of z: the forward and the
+            # backward of the output heads both stream it (csrc/head_train.cu)
+            n_, t_, h_, w_, c_ = z.shape
+            _check(_lib.load().stemseg_upsample_add_f32(_lib.ptr(z), _lib.ptr(y_low), n_, t_, h_, w_, c_, tscale[k],
+                                                        _lib.stream_ptr()))
+            saved["x4"] = z
+            out = D.head_output_x(z, out_spec)
     saved["out_spec"] = out_spec
     D.KEEP = []
     if DEBUG_SAVED is not None:
@@ -189,18 +195,17 @@ def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=T
     g = grad_out.contiguous().to(torch.float32)
 
     # ---- output heads ----------------------------------------------------------------------------------------------
-    m2 = saved["merges"][2]
-    z, y_low = m2["z"], m2["y_low"]
-    n, t, h, w, c3 = z.shape
+    x4 = saved["x4"]
+    n, t, h, w, c3 = x4.shape
     dx = _empty((n, t, h, w, c3), torch.float32, dev)
     d_wout = _empty((spec.n_out, c3), torch.float32, dev)
     d_bout = _empty((spec.n_out,), torch.float32, dev)
-    ws_bytes = lib.stemseg_head_backward_workspace_bytes(c3)
+    ws_bytes = lib.stemseg_head_backward_x_workspace_bytes(c3)
     ws = _empty((ws_bytes,), torch.uint8, dev)
-    _check(lib.stemseg_head_backward(_lib.ptr(z), _lib.ptr(y_low), n, t, h, w, c3, tscale[2], _lib.ptr(spec.weight),
-                                     _lib.ptr(spec.bias), _lib.ptr(spec.activation), spec.n_out, _lib.ptr(g),
-                                     _lib.ptr(dx), _lib.ptr(d_wout), _lib.ptr(d_bout), _lib.ptr(ws), ws_bytes,
-                                     _lib.stream_ptr()))
+    _check(lib.stemseg_head_backward_x(_lib.ptr(x4), n, t, h, w, c3, _lib.ptr(spec.weight), _lib.ptr(spec.bias),
+                                       _lib.ptr(spec.activation), spec.n_out, _lib.ptr(g), _lib.ptr(dx),
+                                       _lib.ptr(d_wout), _lib.ptr(d_bout), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+    _lib.KERNEL_LAUNCHES[0] += 2 * ((spec.n_out - 1) // 8)
     head._scatter_output_grads(d_wout, d_bout, grads)
 
     # ---- merges (conv1x1(cat(up(x), f)) = up(W_a x) + W_b f), highest resolution first -----------------------------

@@ -181,6 +181,26 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
     }
 }
 
+// same result, parallel over rows as well: block = 32 columns x 8 row groups; partial sums of the row groups are added
+// in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) reduce_rows_tiled_kernel(const float* __restrict__ partial, int rows, long long cols,
+                                                                long long row_stride, float* __restrict__ out) {
+    __shared__ double s[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long col = blockIdx.x * 32ll + tx;
+    double a = 0.0;
+    if (col < cols)
+        for (int b = ty; b < rows; b += 8) a += static_cast<double>(partial[static_cast<size_t>(b) * row_stride + col]);
+    s[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && col < cols) {
+        double tot = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) tot += s[r][tx];
+        out[col] = static_cast<float>(tot);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Adjoint of the trilinear up-sampling: dlow[i] = sum_o w(o -> i) dhigh[o]  (gather form, deterministic)
 // ---------------------------------------------------------------------------------------------------------------
@@ -526,22 +546,29 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const void* __restri
     }
 }
 
-// dW partial slices [S][ntaps][cout][cin] (fp32) -> torch layout dst[cout][cin_total][ntaps] at channel offset cin_begin
+// dW partial slices [S][ntaps][cout][cin] (fp32) -> torch layout dst[cout][cin_total][ntaps] at channel offset cin_begin.
+// One block per (cout, 32 input channels): reads are coalesced along cin, the (cin, tap) tile is transposed through
+// shared memory and written as one contiguous run of 32*ntaps floats.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ slices, int s_count, int cout, int ntaps,
                                                            int cin, float* __restrict__ dst, int cin_total, int cin_begin,
                                                            int accumulate) {
-    const long long total = 1ll * cout * ntaps * cin;
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-        const int ci = static_cast<int>(i % cin);
-        const int tap = static_cast<int>((i / cin) % ntaps);
-        const int co = static_cast<int>(i / (1ll * cin * ntaps));
-        // the GEMM writes slices as [k_split][tap][cout][cin]
+    __shared__ float s_tile[32 * 27];
+    const int tiles_ci = (cin + 31) / 32;
+    const int co = blockIdx.x / tiles_ci;
+    const int ci0 = (blockIdx.x % tiles_ci) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int ci = ci0 + tx;
+    for (int tap = ty; tap < ntaps; tap += 8) {
         double a = 0.0;
-        for (int s = 0; s < s_count; ++s)
-            a += slices[((static_cast<size_t>(s) * ntaps + tap) * cout + co) * cin + ci];
-        float* o = dst + (static_cast<size_t>(co) * cin_total + cin_begin + ci) * ntaps + tap;
-        *o = accumulate ? *o + static_cast<float>(a) : static_cast<float>(a);
+        if (ci < cin)
+            for (int s = 0; s < s_count; ++s)
+                a += slices[((static_cast<size_t>(s) * ntaps + tap) * cout + co) * cin + ci];
+        s_tile[tx * ntaps + tap] = static_cast<float>(a);
     }
+    __syncthreads();
+    const int n_ci = cin - ci0 < 32 ? cin - ci0 : 32;
+    float* o = dst + (static_cast<size_t>(co) * cin_total + cin_begin + ci0) * ntaps;
+    for (int i = threadIdx.x; i < n_ci * ntaps; i += 256) o[i] = accumulate ? o[i] + s_tile[i] : s_tile[i];
 }
 
 }  // namespace
@@ -685,7 +712,7 @@ extern "C" int32_t stemseg_channel_sum(const float* x, int64_t rows, int32_t c, 
     const int rws = 256 / quads >= 1 ? 256 / quads : 1;
     const size_t smem = static_cast<size_t>(rws) * c * sizeof(float);
     channel_sum_partial_kernel<<<chunks, quads * rws, smem, stream>>>(x, rows, c, 256, static_cast<float*>(workspace));
-    reduce_rows_kernel<<<grid_cap(c, 256, 1), 256, 0, stream>>>(static_cast<const float*>(workspace), chunks, c, c, out, 0);
+    reduce_rows_tiled_kernel<<<(c + 31) / 32, 256, 0, stream>>>(static_cast<const float*>(workspace), chunks, c, c, out);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
@@ -736,9 +763,11 @@ extern "C" int32_t stemseg_wgrad_reduce(const float* slices, int32_t n_slices, i
                    cin_begin + cin <= cin_total,
                "wgrad_reduce: bad arguments");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const long long total = 1ll * cout * ntaps * cin;
-    wgrad_reduce_kernel<<<grid_cap(total, 256), 256, 0, stream>>>(slices, n_slices, cout, ntaps, cin, dst, cin_total,
-                                                                  cin_begin, accumulate);
+    SS_REQUIRE(ntaps <= 27, "wgrad_reduce: at most 27 taps");
+    const long long blocks = 1ll * cout * ((cin + 31) / 32);
+    SS_REQUIRE(blocks < 0x7FFFFFFFll, "wgrad_reduce: too many blocks");
+    wgrad_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(slices, n_slices, cout, ntaps, cin, dst, cin_total,
+                                                                           cin_begin, accumulate);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

@@ -250,6 +250,21 @@ def head_output(z, y_low, t_scale, spec):
     return out
 
 
+def head_output_x(x, spec):
+    """Training path: output heads over the merged fp32 feature x [n,t,h,w,c] (see csrc/head_train.cu)."""
+    lib = _lib.load()
+    n, t, h, w, c = x.shape
+    if spec.weight.shape[1] != c:
+        raise ValueError("output conv expects %d channels, got %d" % (spec.weight.shape[1], c))
+    with torch.cuda.device(x.device):
+        out = torch.empty((n, spec.n_out, t, h, w), dtype=torch.float32, device=x.device)
+        _check(lib.stemseg_head_output_x(_lib.ptr(x), n, t, h, w, c, _lib.ptr(spec.weight), _lib.ptr(spec.bias),
+                                         _lib.ptr(spec.activation), _lib.ptr(spec.coordinate), spec.n_out,
+                                         spec.time_scale, _lib.ptr(out), _lib.stream_ptr()))
+        _lib.KERNEL_LAUNCHES[0] += (spec.n_out - 1) // 8           # one launch per 8 outputs
+    return out
+
+
 def fused_merge_head_output(act, packed, y_low, t_scale, spec, max_ctas=0):
     """Last merge + output heads in one launch: conv1x1(act) stays in TMEM, its epilogue applies the output convs.
 
