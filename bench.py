@@ -97,6 +97,9 @@ def best_cpu_threads(feats, emb_sd, seed_sd):
     return best
 
 
+REFERENCE_BUDGET_S = 120.0
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -104,12 +107,16 @@ def run_reference_arm(args, rank, world):
     feats = make_features_cpu()
     emb_sd, seed_sd = build_cpu_reference()
     threads = best_cpu_threads(feats, emb_sd, seed_sd)
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(0, min(args.warmup, 3) - 1)):          # best_cpu_threads already ran the step 4 times
         cpu_reference_step(feats, emb_sd, seed_sd)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    # bounded: full clips, but never more than REFERENCE_BUDGET_S of CPU time (a clip takes 0.8-11 s on the hosts seen
+    # so far); the number of clips actually timed is reported in `steps` / `cpu_baseline.sample`
+    steps, t0 = 0, time.perf_counter()
+    while steps < args.steps and (steps < 2 or time.perf_counter() - t0 < REFERENCE_BUDGET_S):
         cpu_reference_step(feats, emb_sd, seed_sd)
+        steps += 1
     dt = time.perf_counter() - t0
+    args.steps = steps
     value = args.steps / dt
     line = {
         "impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
@@ -659,10 +666,10 @@ def run_train_reference(args, rank, world):
     state = build_train_reference()
     for _ in range(max(1, min(args.warmup, 1))):
         train_reference_step(state, feats, masks, ignore)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    steps, t0 = 0, time.perf_counter()
+    while steps < args.steps and (steps < 2 or time.perf_counter() - t0 < REFERENCE_BUDGET_S):
         train_reference_step(state, feats, masks, ignore)
+        steps += 1
     dt = time.perf_counter() - t0
     value = steps / dt
     print(json.dumps({
