@@ -337,8 +337,8 @@ def run_gpu_arm(args, rank, local_rank, world):
     _lib.KERNEL_LAUNCHES[0] = 0
     ms_total, _ = timed(run_resident, args.steps, whole=True)
     launches = _lib.KERNEL_LAUNCHES[0]
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(run_e2e, args.steps, whole=True)
+    clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions
 
     # per-stage breakdown (untimed extra pass on rank 0; informational)
     stages = {}
@@ -818,7 +818,7 @@ def run_train(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])

@@ -344,3 +344,52 @@ def build_davis_pipeline(device, num_frames=8, precision="fp32", in_channels=256
     emb, seedi = emb.to(device).eval(), seedi.to(device).eval()
     clusterer = SequentialClustering(0.5, 0.3, min_seediness_prob, 2, [0.3, 0.3], device)
     return SubclipPipeline(emb, seedi, clusterer)
+
+
+# head settings of the shipped configs (stemseg/config/davis_1.yaml, youtube_vis.yaml, kitti_mots_2.yaml over
+# defaults.yaml:56-86,114-117): embedding mode / size, where seediness comes from, semseg head, clustering threshold
+SHIPPED_CONFIGS = {
+    "davis": dict(dim_mode="xyff", embedding_size=4, seediness_head=True, semseg=None, free_dim_stds=[0.3, 0.3],
+                  min_seediness_prob=0.8),
+    "youtube_vis": dict(dim_mode="xyff", embedding_size=4, seediness_head=False,
+                        semseg=dict(num_classes=41, inter_channels=(256, 256, 256, 256), foreground_channel=True),
+                        free_dim_stds=[0.3, 0.3], min_seediness_prob=0.8),
+    "kitti_mots": dict(dim_mode="xyt", embedding_size=3, seediness_head=False,
+                       semseg=dict(num_classes=3, inter_channels=(256, 256, 128, 128), foreground_channel=True),
+                       free_dim_stds=[], min_seediness_prob=0.95),
+}
+
+
+def build_pipeline(config, device, num_frames=8, precision="fp32", in_channels=256,
+                   inter_channels=(256, 256, 128, 128), semseg_inter_channels=None, num_classes=None,
+                   min_seediness_prob=None, seed=42):
+    """Random-init heads + clusterer wired like build_model() / TrackGenerator do for one of the shipped configs
+    (model_builder.py:268-331, inference/main.py:84-91).  Channel widths can be overridden (tests use small ones)."""
+    from functools import partial
+    import torch.nn as nn
+    from stemseg_b200.clusterers import SequentialClustering
+    from stemseg_b200.heads import EmbeddingHead, SeedinessHead, SemsegHead, get_nb_free_dims
+    cfg = SHIPPED_CONFIGS[config]
+    torch.manual_seed(seed)                                  # model_builder.py:252
+    norm = partial(nn.GroupNorm, 32)
+    emb = EmbeddingHead(in_channels, list(inter_channels), cfg["embedding_size"], tanh_activation=True,
+                        seediness_output=not cfg["seediness_head"], experimental_dims=cfg["dim_mode"],
+                        PoolType=nn.AvgPool3d, NormType=norm, num_frames=num_frames, precision=precision)
+    seedi = None
+    if cfg["seediness_head"]:
+        seedi = SeedinessHead(in_channels, list(inter_channels), PoolType=nn.AvgPool3d, NormType=norm,
+                              num_frames=num_frames, precision=precision).to(device).eval()
+    semseg = None
+    if cfg["semseg"] is not None:
+        sc = cfg["semseg"]
+        semseg = SemsegHead(in_channels, num_classes if num_classes is not None else sc["num_classes"],
+                            inter_channels=list(semseg_inter_channels or sc["inter_channels"]),
+                            feature_scales=[4, 8, 16, 32], foreground_channel=sc["foreground_channel"],
+                            PoolType=nn.AvgPool3d, NormType=norm, num_frames=num_frames,
+                            precision=precision).to(device).eval()
+    emb = emb.to(device).eval()
+    n_free = get_nb_free_dims(cfg["dim_mode"])
+    assert n_free == len(cfg["free_dim_stds"])
+    msp = cfg["min_seediness_prob"] if min_seediness_prob is None else min_seediness_prob
+    clusterer = SequentialClustering(0.5, 0.3, msp, n_free, list(cfg["free_dim_stds"]), device)
+    return SubclipPipeline(emb, seedi, clusterer, semseg_head=semseg)
