@@ -202,6 +202,42 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def time_incumbent_gpu_heads(device, reps=5):
+    """Embedding + seediness heads of the bench clip as torch ops on the GPU (oracle/decoder_oracle.py is the
+    functional form of the reference modules): ms per clip, CUDA events, after warm-up (cuDNN autotune off: the
+    reference does not enable it)."""
+    import torch
+    from oracle import decoder_oracle as do
+    emb_sd, seed_sd = build_cpu_reference()
+    emb_sd = {k: v.to(device) for k, v in emb_sd.items()}
+    seed_sd = {k: v.to(device) for k, v in seed_sd.items()}
+    feats = [f.to(device) for f in (make_features_cpu()[s] for s in (32, 16, 8, 4))]
+    out = {}
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for label, tf32 in (("heads_ms_fp32", False), ("heads_ms_tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    do.embedding_head(emb_sd, feats, T, 4, "xyff", True, False)
+                    do.seediness_head(seed_sd, feats, T)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(reps):
+                    do.embedding_head(emb_sd, feats, T, 4, "xyff", True, False)
+                    do.seediness_head(seed_sd, feats, T)
+                b.record()
+                torch.cuda.synchronize()
+            out[label] = a.elapsed_time(b) / reps
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    out["note"] = "torch %s / cuDNN %s eager, heads only (no gather / clustering), same clip and weights shape" % (
+        torch.__version__, torch.backends.cudnn.version())
+    return out
+
+
 def cluster_fullres_roofline(device, peaks, n=T * HP * WP, e=4, iters=5):
     """SequentialClustering at full resolution (--resize_embeddings, inference/main.py:242-243): the working set
     (80 MB) no longer fits comfortably next to everything else and the kernel is bandwidth-bound.
@@ -416,6 +452,15 @@ def run_gpu_arm(args, rank, local_rank, world):
                   "the plan as a CUDA graph)",
     }
 
+    # the incumbent GPU path, for context: the same heads as plain torch ops (cuDNN conv3d, native GroupNorm / pool /
+    # interpolate -- what the unmodified reference modules run on this GPU), fp32 with and without TF32
+    incumbent = None
+    if world == 1 and not args.no_incumbent:
+        try:
+            incumbent = time_incumbent_gpu_heads(device)
+        except Exception as exc:                     # informational only: never lose the bench line over it
+            incumbent = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     # CPU baseline on a bounded sample (rank 0, N == 1 only)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -458,6 +503,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         "roofline": roofline,
         "roofline_cluster_fullres": cluster_roofline,
         "cpu_baseline": cpu_baseline,
+        "incumbent_gpu": incumbent,
         "stages": stages,
     }
     print(json.dumps(line), flush=True)
@@ -714,12 +760,27 @@ def run_train(args, rank, local_rank, world):
             f.grad = None
         return trainer.step(dev_feats, targets)
 
+    from stemseg_b200.pipeline import HostFeatureStream
+    stager = HostFeatureStream(device)
+    host_clip = {32: host_feats[0], 16: host_feats[1], 8: host_feats[2], 4: host_feats[3],
+                 "masks": host_targets[0]["masks"], "ignore": host_targets[0]["ignore_masks"]}
+
+    def run_e2e(steps):
+        """Pinned host pyramid + targets, double-buffered: the copies of clip i+1 run on the copy stream while clip i
+        trains; the loss is read back (D2H, synchronising) every step."""
+        ticket = stager.submit(host_clip)
+        for i in range(steps):
+            nxt = stager.submit(host_clip) if i + 1 < steps else None
+            buf = stager.get(ticket)
+            out = trainer.step([buf[32], buf[16], buf[8], buf[4]],
+                               [{"masks": buf["masks"], "ignore_masks": buf["ignore"]}])
+            stager.release(ticket)
+            loss = float(out["optimization_losses"]["embedding_loss"].detach())
+            assert loss == loss
+            ticket = nxt
+
     def step_e2e():
-        f = [x.to(device, non_blocking=True).requires_grad_(True) for x in host_feats]
-        t = [{"masks": host_targets[0]["masks"].to(device, non_blocking=True),
-              "ignore_masks": host_targets[0]["ignore_masks"].to(device, non_blocking=True)}]
-        out = trainer.step(f, t)
-        return float(out["optimization_losses"]["embedding_loss"].detach())       # D2H read of the loss
+        run_e2e(1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -752,7 +813,7 @@ def run_train(args, rank, local_rank, world):
     ms_total = timed(step_resident, args.steps)
     launches = _lib.KERNEL_LAUNCHES[0]
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(lambda: run_e2e(args.steps), 1)
 
     # the same step driven through torch autograd (what the reference's training loop does with the B200 heads and
     # loss installed): ~500 launches issued from Python instead of 3 graph replays.  Single-GPU runs only (the
@@ -802,7 +863,8 @@ def run_train(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
-                "note": "pinned host pyramid + targets copied in every step, loss read back every step"},
+                "note": "pinned host pyramid + targets copied in every step (double-buffered on a copy stream), loss "
+                        "read back every step"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
@@ -823,6 +885,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip timing the torch/cuDNN heads on the GPU")
     ap.add_argument("--workload", default="davis480p", choices=["davis480p", "cfg3", "video64", "train"],
                     help="davis480p = BASELINE configs[1] (the contract line); cfg3 / video64 / train = configs[2] / "
                          "configs[3] / configs[4]")

@@ -182,3 +182,57 @@ def test_batched_training_fails_loudly(cuda_device):
     head.load_state_dict(sd, strict=True)
     with pytest.raises(NotImplementedError):
         head([f.to(cuda_device).requires_grad_(True) for f in feats])
+
+
+def test_direct_and_transposed_weight_gradients_agree(cuda_device):
+    """The MN-major direct wgrad kernel against the first implementation (zero-padded transposed copies, K-major
+    operands): two independent data paths to the same tensor-core GEMM, 3x3x3 and 1x1x1, ragged volume."""
+    from stemseg_b200 import autograd as A, decoder as D
+    torch.manual_seed(9)
+    for ksize, cin, cout, t, h, w in ((3, 64, 96, 3, 10, 20), (1, 96, 32, 4, 12, 16), (3, 128, 128, 2, 24, 40)):
+        x = torch.randn(1, cin, t, h, w, device=cuda_device)
+        dy = torch.randn(1, t, h, w, cout, device=cuda_device)
+        xp = D.pack_activation(x, 2)
+        dyp = A._to_planes(dy, 2)
+        outs = {}
+        for mode in ("direct", "transposed"):
+            A.WGRAD_MODE = mode
+            try:
+                dst = torch.empty(cout, cin, ksize ** 3, device=cuda_device)
+                A._wgrad(dy, dyp, xp, ksize, 2, dst, 0)
+                torch.cuda.synchronize()
+                outs[mode] = dst.double().cpu()
+            finally:
+                A.WGRAD_MODE = "direct"
+        ref = torch.nn.grad.conv3d_weight(x.double().cpu(), (cout, cin, ksize, ksize, ksize),
+                                          dy.permute(0, 4, 1, 2, 3).double().cpu(), padding=ksize // 2)
+        ref = ref.reshape(cout, cin, ksize ** 3)
+        for mode, got in outs.items():
+            assert float((got - ref).norm() / ref.norm()) <= 2e-5, (mode, ksize, cin, cout)
+        assert float((outs["direct"] - outs["transposed"]).norm() / ref.norm()) <= 2e-5
+
+
+def test_bf16_precision_gradients(cuda_device):
+    """precision='bf16' (one operand plane, one tensor-core product per MAC): same kernels, bf16-level tolerance."""
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    sd, feats, case = dc.build_case("seediness_t8")
+    head = heads.SeedinessHead(case["in_channels"], case["inter"], NormType=lambda c: nn.GroupNorm(32, c),
+                               num_frames=case["num_frames"], precision="bf16").to(cuda_device)
+    head.load_state_dict(sd, strict=True)
+    fdev = [f.to(cuda_device).requires_grad_(True) for f in feats]
+    out = head(fdev)
+    gen = torch.Generator().manual_seed(4242)
+    r = torch.randn(out.shape, generator=gen, dtype=torch.float64)
+    (out * r.to(device=cuda_device, dtype=torch.float32)).sum().backward()
+    torch.cuda.synchronize()
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    f64 = [f.double().clone().requires_grad_(True) for f in feats]
+    ref = do.seediness_head(sd64, f64, case["num_frames"])
+    (ref * r).sum().backward()
+    assert _rel(out.detach(), ref.detach()) <= 2e-2
+    for fd, fr in zip(fdev, f64):
+        assert _rel(fd.grad, fr.grad) <= 5e-2
+    for name, p in head.named_parameters():
+        if name.endswith(".weight") and p.dim() == 5:
+            assert _rel(p.grad, sd64[name].grad) <= 5e-2, name
