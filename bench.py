@@ -748,7 +748,7 @@ def run_train(args, rank, local_rank, world):
                                 precision=args.precision).to(device)
     crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3], weight_variance_smoothness=10.0,
                          weight_lovasz=1.0, weight_regularization=0.001, weight_seediness=1.0, weight=1.0)
-    trainer = DecoderTrainer({"embedding": emb, "seediness": seedh}, crit)
+    trainer = DecoderTrainer({"embedding": emb, "seediness": seedh}, crit, overlap_heads=not args.no_overlap_heads)
     feats_cpu, masks, ignore = make_train_inputs(rank)
     host_feats = [f.pin_memory() for f in feats_cpu]
     dev_feats = [f.to(device).requires_grad_(True) for f in host_feats]
@@ -885,6 +885,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap-heads", action="store_true",
+                    help="train workload: three graphs with per-head all-reduce overlap instead of two concurrent heads")
     ap.add_argument("--no-incumbent", action="store_true", help="skip timing the torch/cuDNN heads on the GPU")
     ap.add_argument("--workload", default="davis480p", choices=["davis480p", "cfg3", "video64", "train"],
                     help="davis480p = BASELINE configs[1] (the contract line); cfg3 / video64 / train = configs[2] / "

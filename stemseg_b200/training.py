@@ -132,8 +132,12 @@ class DecoderTrainer(object):
     criterion: stemseg_b200.losses.EmbeddingLoss.  Hyper-parameters default to defaults.yaml:17-31."""
 
     def __init__(self, heads, criterion, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True, group=None,
-                 use_graph=True, need_feature_grads=True):
+                 use_graph=True, need_feature_grads=True, overlap_heads=True):
         self.use_graph = use_graph
+        # graph mode with two heads: run the heads' forward (and, after the loss, their backward) concurrently on two
+        # streams inside ONE graph -- the latency-bound small kernels of one head hide under the tensor-core
+        # convolutions of the other.  False: three graphs, per-head all-reduce overlapped with the other head's backward.
+        self.overlap_heads = overlap_heads
         self.need_feature_grads = need_feature_grads
         self.group = group
         self._graphs = {}
@@ -222,6 +226,44 @@ class DecoderTrainer(object):
             for flat in flats:
                 sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
 
+        def seg_both_heads_concurrently():
+            main = torch.cuda.current_stream()
+            side = entry["side_stream"]
+
+            def fork():
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+
+            def join():
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+
+            fork()
+            with torch.cuda.stream(side):                     # second head: forward on the side stream
+                mods[1].invalidate_packed_weights()
+                out1, sv1 = A.training_forward(mods[1], None, in_planes=entry["in_planes"])
+            mods[0].invalidate_packed_weights()
+            out0, sv0 = A.training_forward(mods[0], None, in_planes=entry["in_planes"])
+            join()
+            emb_map = torch.cat((out0, out1), dim=1)          # model_builder.py:198-201
+            losses, grad = embedding_loss_and_gradient(emb_map, entry["masks"], entry["ignore"], self.criterion)
+            entry["losses"] = losses
+            c0 = out0.shape[1]
+            state["grads_out"], state["saved"], state["outs"] = [grad[:, :c0], grad[:, c0:]], [sv0, sv1], [out0, out1]
+            fork()
+            with torch.cuda.stream(side):
+                fg1, _ = A.training_backward(mods[1], sv1, state["grads_out"][1], grad_dst=self._grad_slots(flats[1]),
+                                             need_feature_grads=self.need_feature_grads)
+            fg0, _ = A.training_backward(mods[0], sv0, state["grads_out"][0], grad_dst=self._grad_slots(flats[0]),
+                                         need_feature_grads=self.need_feature_grads)
+            join()
+            state["fg"] = (fg0, fg1)
+            entry["feature_grads"] = [a + b for a, b in zip(fg0, fg1)] if self.need_feature_grads else None
+
+        if self.overlap_heads and len(mods) == 2:
+            return [seg_both_heads_concurrently, seg_optimizer]
         return [seg_forward_loss_backward_last, seg_backward_first, seg_optimizer]
 
     def _capture(self, feats, targets):
@@ -232,13 +274,14 @@ class DecoderTrainer(object):
         entry = {"in_planes": [D.pack_activation(f.detach(), planes) for f in feats],
                  "masks": masks.to(device=dev, dtype=torch.uint8).contiguous().clone(),
                  "ignore": targets[0]["ignore_masks"].to(device=dev, dtype=torch.uint8).contiguous().clone()}
+        entry["side_stream"] = torch.cuda.Stream(device=dev)
         segments = self._segments(entry)
         # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, allocator) -- without the optimiser
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            segments[0]()
-            segments[1]()
+            for seg in segments[:-1]:
+                seg()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graphs, pool = [], None
@@ -273,17 +316,22 @@ class DecoderTrainer(object):
             entry["masks"].copy_(masks, non_blocking=True)
             entry["ignore"].copy_(ignore, non_blocking=True)
             pending = []
-            (g1, k1), (g2, k2), (g3, k3) = entry["graphs"]
-            g1.replay()
-            if self.world > 1:                 # gradients of the last head are complete: reduce while g2 runs
-                pending.append(dist.all_reduce(self.flats[-1].grad, group=self.group, async_op=True))
-            g2.replay()
-            if self.world > 1 and len(self.flats) > 1:
-                pending.append(dist.all_reduce(self.flats[0].grad, group=self.group, async_op=True))
+            graphs = entry["graphs"]
+            if len(graphs) == 2:               # both heads in one graph, then both reductions
+                graphs[0][0].replay()
+                if self.world > 1:
+                    pending = [dist.all_reduce(f.grad, group=self.group, async_op=True) for f in self.flats]
+            else:
+                graphs[0][0].replay()
+                if self.world > 1:             # gradients of the last head are complete: reduce while g2 runs
+                    pending.append(dist.all_reduce(self.flats[-1].grad, group=self.group, async_op=True))
+                graphs[1][0].replay()
+                if self.world > 1 and len(self.flats) > 1:
+                    pending.append(dist.all_reduce(self.flats[0].grad, group=self.group, async_op=True))
             for work in pending:
                 work.wait()
-            g3.replay()
-            _lib.KERNEL_LAUNCHES[0] += k1 + k2 + k3
+            graphs[-1][0].replay()
+            _lib.KERNEL_LAUNCHES[0] += sum(k for _, k in graphs)
             for m in self._modules():
                 m.invalidate_packed_weights()  # the packed copies inside the graph pool predate this step's update
         losses = entry["losses"]
