@@ -445,6 +445,10 @@ def run_gpu_arm(args, rank, local_rank, world):
         "launch_ms": dom_ms,
         "tensor_pipe_products_per_mac": planes_products,
         "tensor_pipe_frac": achieved * planes_products / peaks["bf16_tflops_sustained"],
+        # fp32-parity arithmetic issues 3 bf16 tensor-core products per algorithmic MAC (hi*hi + hi*lo + lo*hi), so the
+        # algorithmic rate cannot exceed peak / 3; `frac` above is against the full bf16 peak as the contract asks
+        "algorithmic_ceiling_tflops": peaks["bf16_tflops_sustained"] / planes_products,
+        "frac_of_algorithmic_ceiling": achieved * planes_products / peaks["bf16_tflops_sustained"],
         "launches_per_step": dom_count_per_step,
         "share_of_step": sum(dom_times) / args.steps / (ms_total / args.steps),
         "all_conv_share_of_step": conv_ms_per_step / (ms_total / args.steps),
