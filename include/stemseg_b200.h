@@ -322,6 +322,14 @@ int32_t stemseg_group_norm_backward(float* d_norm_to_dy, const float* y, const f
                                     int32_t n, int64_t spatial, int32_t c, int32_t channels_per_group,
                                     float* dgamma_dbeta, float* group_terms, void* workspace, size_t workspace_bytes,
                                     void* stream);
+/* GroupNorm backward with the fused tail: dy is written only as bf16 planes [P][n][spatial][c] (what dgrad / wgrad
+ * consume) and its per-channel sums (the conv bias gradient) come out of the same pass; d_norm is left untouched */
+size_t stemseg_group_norm_backward_planes_workspace_bytes(int32_t n, int64_t spatial, int32_t c);
+int32_t stemseg_group_norm_backward_planes(const float* d_norm, const float* y, const float* mean_rstd,
+                                           const float* gamma, int32_t n, int64_t spatial, int32_t c,
+                                           int32_t channels_per_group, float* dgamma_dbeta, float* group_terms,
+                                           void* dy_planes, int32_t planes, float* d_bias, void* workspace,
+                                           size_t workspace_bytes, void* stream);
 /* out[c] = sum over rows of x[rows][c] (bias gradients), deterministic */
 size_t stemseg_channel_sum_workspace_bytes(int64_t rows, int32_t c);
 int32_t stemseg_channel_sum(const float* x, int64_t rows, int32_t c, float* out, void* workspace, size_t workspace_bytes,

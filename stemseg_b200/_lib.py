@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -91,6 +91,10 @@ PROTOTYPES = {
     "stemseg_group_norm_backward_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "stemseg_group_norm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
                                               c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_group_norm_backward_planes_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "stemseg_group_norm_backward_planes": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
+                                                     c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                                     c_size_t, c_void_p]),
     "stemseg_channel_sum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "stemseg_channel_sum": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_to_planes": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
@@ -150,7 +154,7 @@ KERNELS_PER_CALL = {
     "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
     "stemseg_conv3d_wgrad_direct": 1,
     "stemseg_scale_by_device_scalar": 1, "stemseg_sgd_step": 1,
-    "stemseg_upsample_add_f32": 1, "stemseg_head_output_x": 1, "stemseg_head_backward_x": 2,
+    "stemseg_group_norm_backward_planes": 4, "stemseg_upsample_add_f32": 1, "stemseg_head_output_x": 1, "stemseg_head_backward_x": 2,
     # stemseg_embedding_loss launches a shape-dependent number of kernels: counted by losses.py
 }
 

@@ -143,11 +143,11 @@ def _wgrad(dy, dy_planes, x_planes, kernel_size, planes, dst, cin_begin):
 
     dy_planes: the same gradient as bf16 planes (shared with the dgrad convolution)."""
     lib = _lib.load()
-    _, t, h, w, co = dy.shape
+    t, h, w, co = dy_planes.t, dy_planes.h, dy_planes.w, dy_planes.c
     ci = x_planes.c
     assert (x_planes.t, x_planes.h, x_planes.w) == (t, h, w)
     taps = 27 if kernel_size == 3 else 1
-    dev = dy.device
+    dev = dy_planes.tensor.device
     if WGRAD_MODE == "direct":
         ks = lib.stemseg_wgrad_direct_k_splits(co, ci, t, h, w, kernel_size)
         slices = _empty((ks, taps, co, ci), torch.float32, dev)
@@ -241,27 +241,40 @@ def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=T
             _check(lib.stemseg_pool_relu_backward(_lib.ptr(d), _lib.ptr(y), _lib.ptr(st["scale_shift"]), nn_, t_, h_, w_,
                                                   c_, 1 if st["pool"] else 0, _lib.ptr(dn), _lib.stream_ptr()))
             wname, bname = "%s.%d.weight" % (name, 4 * j), "%s.%d.bias" % (name, 4 * j)
+            d_bias = _empty((c_,), torch.float32, dev)
+            fused_tail = st["mean_rstd"] is not None and WGRAD_MODE == "direct"
             if st["mean_rstd"] is not None:
                 groups = st["mean_rstd"].shape[1]
                 dgb = _empty((nn_, c_, 2), torch.float32, dev)
                 gterms = _empty((nn_, groups, 2), torch.float32, dev)
-                wsb = lib.stemseg_group_norm_backward_workspace_bytes(nn_, t_ * h_ * w_, c_)
-                wsg = _empty((wsb,), torch.uint8, dev)
-                _check(lib.stemseg_group_norm_backward(_lib.ptr(dn), _lib.ptr(y), _lib.ptr(st["mean_rstd"]),
-                                                       _lib.ptr(st["gamma"]), nn_, t_ * h_ * w_, c_, c_ // groups,
-                                                       _lib.ptr(dgb), _lib.ptr(gterms), _lib.ptr(wsg), wsb,
-                                                       _lib.stream_ptr()))
+                if fused_tail:
+                    # dy only as bf16 planes (+ its channel sums = the bias gradient), never in fp32
+                    dy = None
+                    dy_p = D.Planes(_empty((planes, nn_, t_, h_, w_, c_), torch.bfloat16, dev), nn_, t_, h_, w_, c_)
+                    wsb = lib.stemseg_group_norm_backward_planes_workspace_bytes(nn_, t_ * h_ * w_, c_)
+                    wsg = _empty((wsb,), torch.uint8, dev)
+                    _check(lib.stemseg_group_norm_backward_planes(
+                        _lib.ptr(dn), _lib.ptr(y), _lib.ptr(st["mean_rstd"]), _lib.ptr(st["gamma"]), nn_, t_ * h_ * w_, c_,
+                        c_ // groups, _lib.ptr(dgb), _lib.ptr(gterms), _lib.ptr(dy_p.tensor), planes, _lib.ptr(d_bias),
+                        _lib.ptr(wsg), wsb, _lib.stream_ptr()))
+                else:
+                    wsb = lib.stemseg_group_norm_backward_workspace_bytes(nn_, t_ * h_ * w_, c_)
+                    wsg = _empty((wsb,), torch.uint8, dev)
+                    _check(lib.stemseg_group_norm_backward(_lib.ptr(dn), _lib.ptr(y), _lib.ptr(st["mean_rstd"]),
+                                                           _lib.ptr(st["gamma"]), nn_, t_ * h_ * w_, c_, c_ // groups,
+                                                           _lib.ptr(dgb), _lib.ptr(gterms), _lib.ptr(wsg), wsb,
+                                                           _lib.stream_ptr()))
                 grads["%s.%d.weight" % (name, 4 * j + 1)] = dgb[0, :, 0].contiguous()
                 grads["%s.%d.bias" % (name, 4 * j + 1)] = dgb[0, :, 1].contiguous()
-            dy = dn                                               # GroupNorm backward ran in place
-            d_bias = _empty((c_,), torch.float32, dev)
-            wsb = lib.stemseg_channel_sum_workspace_bytes(t_ * h_ * w_, c_)
-            wsc = _empty((wsb,), torch.uint8, dev)
-            _check(lib.stemseg_channel_sum(_lib.ptr(dy), t_ * h_ * w_, c_, _lib.ptr(d_bias), _lib.ptr(wsc), wsb,
-                                           _lib.stream_ptr()))
+            if not fused_tail:
+                dy = dn                                           # GroupNorm backward ran in place (or no norm)
+                wsb = lib.stemseg_channel_sum_workspace_bytes(t_ * h_ * w_, c_)
+                wsc = _empty((wsb,), torch.uint8, dev)
+                _check(lib.stemseg_channel_sum(_lib.ptr(dy), t_ * h_ * w_, c_, _lib.ptr(d_bias), _lib.ptr(wsc), wsb,
+                                               _lib.stream_ptr()))
+                dy_p = _to_planes(dy, planes)
             grads[bname] = d_bias
             wgrad_dst = _dst(grad_dst, wname, params)
-            dy_p = _to_planes(dy, planes)
             _wgrad(dy, dy_p, st["a_in"], 3, planes, wgrad_dst.view(wgrad_dst.shape[0], wgrad_dst.shape[1], 27), 0)
             grads[wname] = wgrad_dst
             if j == 0 and not need_feature_grads:                    # frozen backbone: skip the largest dgrad

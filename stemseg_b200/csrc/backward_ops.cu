@@ -441,6 +441,59 @@ __global__ void __launch_bounds__(256) gn_backward_apply_kernel(float* __restric
     }
 }
 
+// Fused tail of the GroupNorm backward: dy = rstd (gamma dn - A - x_hat B) is written ONLY as bf16 planes (hi / lo) --
+// the form both consumers want (dgrad convolution and direct wgrad) -- and summed per channel on the way (the conv
+// bias gradient).  dy is never materialised in fp32: one read of dn and y, one 4-byte-per-element write, instead of
+// apply (read 8 B, write 4 B) + channel sum (read 4 B) + plane conversion (read 4 B, write 4 B).
+// Block = one chunk of kApChunk voxels; bias partials [chunks][c] are reduced in a fixed order afterwards.
+constexpr int kApChunk = 256;
+
+__global__ void __launch_bounds__(256) gn_backward_apply_planes_kernel(
+    const float* __restrict__ dn, const float* __restrict__ y, const float* __restrict__ mean_rstd,
+    const float* __restrict__ group_terms, const float* __restrict__ gamma, long long spatial, long long rows_total, int c,
+    int cpg, __nv_bfloat16* __restrict__ dst, size_t plane_elems, int planes, float* __restrict__ bias_partial) {
+    extern __shared__ float s_acc[];
+    const int quads = c / 4, groups = c / cpg;
+    const int rows = blockDim.x / quads;
+    const int q = threadIdx.x % quads, r = threadIdx.x / quads;
+    const long long v0 = 1ll * blockIdx.x * kApChunk;
+    long long v1 = v0 + kApChunk;
+    if (v1 > rows_total) v1 = rows_total;
+    float g4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g4[k] = gamma[4 * q + k];
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long v = v0 + r; v < v1; v += rows) {
+        const int nn = static_cast<int>(v / spatial);
+        const long long i = v * quads + q;
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dn) + i);
+        const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + i);
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+        const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = (4 * q + k) / cpg;
+            const float* mr = mean_rstd + (static_cast<size_t>(nn) * groups + g) * 2;
+            const float* gt = group_terms + (static_cast<size_t>(nn) * groups + g) * 2;
+            const float xh = (yv[k] - mr[0]) * mr[1];
+            const float o = mr[1] * (g4[k] * dv[k] - gt[0] - xh * gt[1]);      // same expression as gn_backward_apply
+            s[k] += o;
+            split_bf16_b(o, hi[k], lo[k]);
+        }
+        *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<uint2*>(hi);
+        if (planes == 2) *reinterpret_cast<uint2*>(dst + plane_elems + i * 4) = *reinterpret_cast<uint2*>(lo);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_acc[r * c + 4 * q + k] = s[k];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float a = 0.f;
+        for (int rr = 0; rr < rows; ++rr) a += s_acc[rr * c + ch];
+        bias_partial[static_cast<size_t>(blockIdx.x) * c + ch] = a;
+    }
+}
+
 // per-channel sums of an NDHWC fp32 tensor (bias gradients): partial [chunks][c], then reduce_rows
 __global__ void __launch_bounds__(256) channel_sum_partial_kernel(const float* __restrict__ x, long long rows_total, int c,
                                                                   int chunk_rows, float* __restrict__ partial) {
@@ -689,6 +742,54 @@ extern "C" int32_t stemseg_group_norm_backward(float* d_norm_to_dy, const float*
     const long long total_quads = 1ll * n * spatial * quads;
     gn_backward_apply_kernel<<<grid_cap(total_quads, 256), 256, 0, stream>>>(d_norm_to_dy, y, mean_rstd, group_terms, gamma,
                                                                             spatial, c, channels_per_group, total_quads);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}
+
+extern "C" size_t stemseg_group_norm_backward_planes_workspace_bytes(int32_t n, int64_t spatial, int32_t c) {
+    const size_t a = stemseg_group_norm_backward_workspace_bytes(n, spatial, c);
+    const long long chunks = (static_cast<long long>(n) * spatial + kApChunk - 1) / kApChunk;
+    return a + align_up(static_cast<size_t>(chunks) * c * sizeof(float), 256);
+}
+
+extern "C" int32_t stemseg_group_norm_backward_planes(const float* d_norm, const float* y, const float* mean_rstd,
+                                                      const float* gamma, int32_t n, int64_t spatial, int32_t c,
+                                                      int32_t channels_per_group, float* dgamma_dbeta, float* group_terms,
+                                                      void* dy_planes, int32_t planes, float* d_bias, void* workspace,
+                                                      size_t workspace_bytes, void* stream_) {
+    SS_REQUIRE(d_norm && y && mean_rstd && gamma && dgamma_dbeta && group_terms && dy_planes && d_bias && workspace,
+               "group_norm_backward_planes: null pointer");
+    SS_REQUIRE(n >= 1 && spatial >= 1 && c >= 4 && c % 4 == 0 && c <= 1024, "group_norm_backward_planes: bad shape");
+    SS_REQUIRE(channels_per_group >= 1 && channels_per_group <= 512 && c % channels_per_group == 0,
+               "group_norm_backward_planes: bad group size");
+    SS_REQUIRE(planes == 1 || planes == 2, "group_norm_backward_planes: planes must be 1 or 2");
+    SS_REQUIRE(al16(d_norm) && al16(y) && al16(dy_planes), "group_norm_backward_planes: alignment");
+    const size_t need = stemseg_group_norm_backward_planes_workspace_bytes(n, spatial, c);
+    if (workspace_bytes < need) {
+        set_error("group_norm_backward_planes: workspace %zu < %zu bytes", workspace_bytes, need);
+        return STEMSEG_ERR_WORKSPACE;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int chunks = static_cast<int>((spatial + kGbChunk - 1) / kGbChunk);
+    const int quads = c / 4;
+    int rows = 256 / quads;
+    if (rows < 1) rows = 1;
+    const int threads = quads * rows;
+    const size_t smem = static_cast<size_t>(rows) * c * 2 * sizeof(float);
+    SS_REQUIRE(threads <= 1024 && smem <= 48 * 1024, "group_norm_backward_planes: channel count %d unsupported", c);
+    float* gn_ws = static_cast<float*>(workspace);
+    float* bias_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                              stemseg_group_norm_backward_workspace_bytes(n, spatial, c));
+    gn_backward_partial_kernel<<<dim3(chunks, n), threads, smem, stream>>>(d_norm, y, mean_rstd, spatial, c,
+                                                                           channels_per_group, kGbChunk, gn_ws, chunks);
+    gn_backward_finalize_kernel<<<dim3(c / channels_per_group, n), 256, 0, stream>>>(
+        gn_ws, chunks, c, channels_per_group, spatial, gamma, dgamma_dbeta, group_terms);
+    const long long rows_total = static_cast<long long>(n) * spatial;
+    const int ap_chunks = static_cast<int>((rows_total + kApChunk - 1) / kApChunk);
+    gn_backward_apply_planes_kernel<<<ap_chunks, threads, static_cast<size_t>(rows) * c * sizeof(float), stream>>>(
+        d_norm, y, mean_rstd, group_terms, gamma, spatial, rows_total, c, channels_per_group,
+        static_cast<__nv_bfloat16*>(dy_planes), static_cast<size_t>(rows_total) * c, planes, bias_ws);
+    reduce_rows_tiled_kernel<<<(c + 31) / 32, 256, 0, stream>>>(bias_ws, ap_chunks, c, c, d_bias);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
