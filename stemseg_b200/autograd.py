@@ -6,8 +6,13 @@ stemseg_b200/decoder.py run eagerly with its intermediates kept, and the backwar
 
   * dgrad of every convolution = the tcgen05 convolution kernel itself on the gradient planes with flipped /
     transposed weights (``stemseg_pack_conv_weight_dgrad``);
-  * wgrad = the same kernel in GEMM mode on zero-padded transposed planes (``stemseg_conv3d_wgrad``);
-  * output heads, trilinear adjoint, AvgPool/ReLU and GroupNorm backward: csrc/backward_ops.cu.
+  * wgrad = a tcgen05 GEMM over the voxel index with MN-major operands read straight from the NDHWC planes
+    (``stemseg_conv3d_wgrad_direct``; the first implementation on zero-padded transposed planes,
+    ``stemseg_conv3d_wgrad``, stays selectable with STEMSEG_WGRAD=transposed as a cross-check);
+  * output heads over the fp32 merged feature: csrc/head_train.cu; trilinear adjoint, AvgPool/ReLU and GroupNorm
+    backward (whose tail writes the conv-output gradient only as bf16 planes + its channel sums): csrc/backward_ops.cu.
+The same two functions (``training_forward`` / ``training_backward``) serve torch autograd (``HeadFunction``) and the
+CUDA-graph trainer (stemseg_b200/training.py), which calls them without the autograd engine.
 
 Gradients flow to the four feature maps (so the torch backbone trains as usual) and to every head parameter, which is
 all DistributedDataParallel needs: its gradient all-reduce hooks fire on the parameters' ``.grad`` as with the

@@ -187,7 +187,8 @@ class DecoderTrainer(object):
         return {names[id(p)]: flat.grad[off:off + p.numel()].view_as(p) for p, off in zip(flat.params, flat.offsets)}
 
     def _segments(self, entry):
-        """The three captured segments as closures over the static buffers of `entry`."""
+        """The captured segments (closures over the static buffers of `entry`): [both heads concurrently, optimiser]
+        or, with overlap_heads=False, [forward + loss + backward of the last head, backward of the first, optimiser]."""
         from stemseg_b200 import autograd as A
         from stemseg_b200.losses import embedding_loss_and_gradient
         mods, flats = self._modules(), self.flats
