@@ -388,6 +388,22 @@ int32_t stemseg_embedding_loss(const float* head_out, const float* seediness, co
                                float w_lovasz, float w_variance_smoothness, float w_seediness, float w, float* losses,
                                float* d_head_out, float* d_seediness, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses of the semantic-segmentation head, loss AND gradient, one sequence per call
+ *   replaces CrossEntropyLoss.forward          stemseg/modeling/losses/cross_entropy.py:13-49
+ *            TrainingModel.compute_fg_loss     stemseg/modeling/model_builder.py:210-244
+ * class_logits: channel c of voxel v at class_logits[c * class_stride + v] (the [T,cls,H,W] view the reference passes
+ * has exactly this form), n_classes channels; fg_logits [voxels]; class_ids [voxels] int64 (must lie in
+ * [0, n_classes), the reference raises otherwise); ignore [voxels] uint8 or NULL.  Either term is skipped when its
+ * logits pointer is NULL.  losses[2] = {class loss (unweighted), foreground loss}; the gradients are those of
+ * w_semseg * losses[0] + w_foreground * losses[1].  Quirk kept: the class loss is a plain mean over ALL voxels times
+ * S / S (S = non-ignored voxels): ignored voxels count, S = 0 gives NaN.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t stemseg_semseg_loss_workspace_bytes(void);
+int32_t stemseg_semseg_loss(const float* class_logits, int64_t class_stride, int32_t n_classes, const float* fg_logits,
+                            const int64_t* class_ids, const uint8_t* ignore, int64_t voxels, float w_semseg,
+                            float w_foreground, float* losses, float* d_class, int64_t d_class_stride, float* d_fg,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* x[i] *= *scalar (scalar in device memory: chain-rule factor of loss.backward() without a host round trip) */
 int32_t stemseg_scale_by_device_scalar(float* x, int64_t n, const float* scalar, void* stream);
 

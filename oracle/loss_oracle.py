@@ -144,3 +144,48 @@ def loss_from_head_output(out, masks, ignore, embedding_size, n_free, free_dim_s
     return embedding_loss_sequence(flat[:, :embedding_size], flat[:, embedding_size:embedding_size + v],
                                    flat[:, embedding_size + v], masks.reshape(masks.shape[0], -1).long(),
                                    ignore.reshape(-1), free_dim_stds, **weights)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# semantic-segmentation head losses (YouTube-VIS / KITTI-MOTS configs)
+# --------------------------------------------------------------------------------------------------------------
+def semseg_losses_sequence(head_out, semseg_masks, ignore, foreground_channel=True):
+    """One sequence.  head_out [C, T, H, W] = the semseg head's output (class logits, then the foreground logit when
+    foreground_channel); semseg_masks [T, H, W] int64 class ids; ignore [T, H, W] bool.
+    -> dict(semseg, foreground) following
+      * CrossEntropyLoss.forward     stemseg/modeling/losses/cross_entropy.py:13-49
+      * TrainingModel.compute_fg_loss  stemseg/modeling/model_builder.py:210-244
+      * the permute / split in front of them  model_builder.py:180, :121-122
+    Quirk preserved: F.cross_entropy is called with its default 'mean' reduction, so the ignore mask multiplies a SCALAR
+    and cancels out -- ignored voxels count in the class loss (cross_entropy.py:36-42); only the foreground loss really
+    masks them."""
+    import torch.nn.functional as F
+    logits = head_out.permute(1, 0, 2, 3)                                       # [T, C, H, W]  (model_builder.py:180)
+    fg_logits = None
+    if foreground_channel:
+        logits, fg_logits = logits.split((logits.shape[1] - 1, 1), dim=1)       # model_builder.py:121
+        fg_logits = fg_logits.squeeze(1)
+    nonignore = 1. - ignore.to(head_out.dtype)
+    seq = F.cross_entropy(logits, semseg_masks)
+    seq = seq * nonignore
+    out = {"semseg": seq.sum() / nonignore.sum().detach(), "foreground": None}
+    if fg_logits is not None:
+        fg_target = (semseg_masks > 0).to(head_out.dtype)
+        bce = F.binary_cross_entropy_with_logits(fg_logits, fg_target, reduction="none")
+        out["foreground"] = (bce * nonignore).sum() / nonignore.sum().detach()
+    return out
+
+
+def seeded_semseg_case(seed, t, h, w, num_classes, foreground_channel=True, ignore_frac=0.1):
+    """-> dict(out [1, C, T, H, W] fp32 'semseg head output', semseg_masks [T,H,W] int64, ignore [T,H,W] bool)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    c = num_classes + (1 if foreground_channel else 0)
+    out = (1.5 * rng.standard_normal((1, c, t, h, w))).astype(np.float32)
+    # blocky class map with a large background (class 0) share
+    coarse = rng.integers(0, num_classes, size=(t, (h + 3) // 4, (w + 3) // 4))
+    coarse[rng.random(coarse.shape) < 0.5] = 0
+    masks = np.repeat(np.repeat(coarse, 4, axis=1), 4, axis=2)[:, :h, :w].astype(np.int64)
+    ignore = rng.random((t, h, w)) < ignore_frac
+    return {"out": torch.from_numpy(out), "semseg_masks": torch.from_numpy(masks), "ignore": torch.from_numpy(ignore),
+            "num_classes": num_classes, "foreground_channel": foreground_channel}

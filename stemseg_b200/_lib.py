@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -113,6 +113,9 @@ PROTOTYPES = {
     "stemseg_embedding_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                          ctypes.POINTER(c_float), c_float, c_float, c_float, c_float, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stemseg_semseg_loss_workspace_bytes": (c_size_t, []),
+    "stemseg_semseg_loss": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                      c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_scale_by_device_scalar": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "stemseg_sgd_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32,
                                    c_void_p]),
@@ -154,7 +157,7 @@ KERNELS_PER_CALL = {
     "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
     "stemseg_conv3d_wgrad_direct": 1,
     "stemseg_scale_by_device_scalar": 1, "stemseg_sgd_step": 1,
-    "stemseg_group_norm_backward_planes": 4, "stemseg_upsample_add_f32": 1, "stemseg_head_output_x": 1, "stemseg_head_backward_x": 2,
+    "stemseg_group_norm_backward_planes": 4, "stemseg_semseg_loss": 2, "stemseg_upsample_add_f32": 1, "stemseg_head_output_x": 1, "stemseg_head_backward_x": 2,
     # stemseg_embedding_loss launches a shape-dependent number of kernels: counted by losses.py
 }
 

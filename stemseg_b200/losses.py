@@ -23,6 +23,8 @@ LOSS_EMBEDDING = "embedding_loss"
 LOSS_LOVASZ = "lovasz_loss"
 LOSS_SEEDINESS = "seediness_loss"
 LOSS_VARIANCE_SMOOTHNESS = "variance_smoothness_loss"
+LOSS_SEMSEG = "semantic_segmentation_loss"
+LOSS_FOREGROUND = "foreground"
 OUTPUT_OPTIMIZATION_LOSSES = "optimization_losses"
 OUTPUT_OTHERS = "others"
 
@@ -149,3 +151,116 @@ class EmbeddingLoss(nn.Module):
         output_dict[OUTPUT_OTHERS] = {LOSS_LOVASZ: losses[1].detach(), LOSS_VARIANCE_SMOOTHNESS: losses[2].detach(),
                                       LOSS_SEEDINESS: losses[3].detach()}
         return losses[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# semantic-segmentation head losses (YouTube-VIS / KITTI-MOTS configs)
+# ----------------------------------------------------------------------------------------------------------------------
+def semseg_loss_and_gradient(class_logits, fg_logits, class_ids, ignore, w_semseg=1.0, w_foreground=1.0,
+                             grad_out=None):
+    """One C call (csrc/semseg_loss.cu).  class_logits [T,cls,H,W] or None, fg_logits [T,H,W] or None, class_ids
+    [T,H,W] int64, ignore [T,H,W] bool/uint8 or None -- fp32 CUDA.  Returns (losses [2] = class loss, foreground loss;
+    d(w_semseg*class + w_foreground*fg)/d class_logits (same shape / strides as a [T,cls,H,W] view of a channels-first
+    buffer) or None; d/d fg_logits or None).  grad_out: optional contiguous [cls(+1),T,H,W] tensor that receives both
+    gradients (class channels first, then the foreground channel) -- the layout the head's backward consumes."""
+    lib = _lib.load()
+    ref = class_logits if class_logits is not None else fg_logits
+    if ref is None:
+        raise ValueError("neither class nor foreground logits given")
+    if ref.dtype != torch.float32 or not ref.is_cuda:
+        raise ValueError("the semseg losses need fp32 CUDA logits (got %s on %s); there is no CPU path" % (
+            ref.dtype, ref.device))
+    dev = ref.device
+    with torch.cuda.device(dev):
+        ids = class_ids.to(device=dev, dtype=torch.int64).contiguous()
+        voxels = ids.numel()
+        ig = None if ignore is None else ignore.to(device=dev, dtype=torch.uint8).contiguous()
+        cls_ptr, cls_stride, n_cls, d_cls, d_cls_view = None, 0, 0, None, None
+        if class_logits is not None:
+            t, n_cls, h, w = class_logits.shape
+            x = class_logits
+            if not (x.stride(3) == 1 and x.stride(2) == w and x.stride(0) == h * w and x.stride(1) >= voxels):
+                x = x.permute(1, 0, 2, 3).contiguous().permute(1, 0, 2, 3)       # channels-first storage
+            cls_ptr, cls_stride = x, x.stride(1)
+            d_cls = grad_out[:n_cls] if grad_out is not None else \
+                torch.empty((n_cls, t, h, w), dtype=torch.float32, device=dev)
+            d_cls_view = d_cls.permute(1, 0, 2, 3)
+        fg, d_fg = None, None
+        if fg_logits is not None:
+            fg = fg_logits.contiguous()
+            d_fg = grad_out[n_cls] if grad_out is not None else torch.empty_like(fg)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        ws_bytes = lib.stemseg_semseg_loss_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.stemseg_semseg_loss(_lib.ptr(cls_ptr), cls_stride, n_cls, _lib.ptr(fg), _lib.ptr(ids), _lib.ptr(ig),
+                                           voxels, float(w_semseg), float(w_foreground), _lib.ptr(losses), _lib.ptr(d_cls),
+                                           voxels, _lib.ptr(d_fg), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+    return losses, d_cls_view, d_fg
+
+
+class _SemsegLossFunction(torch.autograd.Function):
+    """(logits) -> losses [2]; term = 0: class logits [T,cls,H,W], term = 1: foreground logits [T,H,W]."""
+
+    @staticmethod
+    def forward(ctx, logits, class_ids, ignore, term):
+        if term == 0:
+            losses, ctx.grad, _ = semseg_loss_and_gradient(logits.detach(), None, class_ids, ignore)
+        else:
+            losses, _, ctx.grad = semseg_loss_and_gradient(None, logits.detach(), class_ids, ignore)
+        ctx.term = term
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        lib = _lib.load()
+        grad, ctx.grad = ctx.grad, None
+        g = grad_losses.detach().to(torch.float32)[ctx.term:ctx.term + 1].contiguous()
+        base = grad if grad.is_contiguous() else grad.permute(1, 0, 2, 3)      # the channels-first storage
+        with torch.cuda.device(grad.device):
+            _lib.check(lib.stemseg_scale_by_device_scalar(_lib.ptr(base), base.numel(), _lib.ptr(g), _lib.stream_ptr()))
+        return grad, None, None, None
+
+
+def _one_sequence(logits, targets):
+    if logits.shape[0] != 1 or len(targets) != 1:
+        raise NotImplementedError("the B200 semseg losses handle one sequence per call (batch 1), like the reference's "
+                                  "MAX_SAMPLES_PER_GPU = 1")
+    gt, ignore = targets[0]["semseg_masks"], targets[0]["ignore_masks"]
+    assert gt.shape[-2:] == logits.shape[-2:], \
+        "Shape mismatch between ground truth semseg masks {} and predicted semseg masks {}".format(gt.shape, logits.shape)
+    assert gt.shape[-2:] == ignore.shape[-2:], \
+        "Shape mismatch between ground truth semseg masks {} and ignore masks {} ".format(gt.shape, ignore.shape)
+    return gt, ignore
+
+
+class CrossEntropyLoss(nn.Module):
+    """Mirror of stemseg/modeling/losses/cross_entropy.py:9-49 (registered as SEMSEG_LOSS_REGISTRY["CrossEntropy"],
+    model_builder.py:26): forward(semseg_logits [N,T,cls,H,W], targets, output_dict)."""
+
+    def __init__(self, weight_semseg=None):
+        super().__init__()
+        self._weight = weight_semseg
+
+    def _weight_semseg(self):
+        if self._weight is not None:
+            return float(self._weight)
+        try:
+            from stemseg.config import cfg                     # cross_entropy.py:49 reads it at call time
+            return float(cfg.TRAINING.LOSSES.WEIGHT_SEMSEG)
+        except ImportError:
+            return 1.0
+
+    def forward(self, semseg_logits, targets, output_dict):
+        gt, ignore = _one_sequence(semseg_logits, targets)
+        losses = _SemsegLossFunction.apply(semseg_logits[0], gt, ignore, 0)
+        output_dict.setdefault(OUTPUT_OTHERS, {})[LOSS_SEMSEG] = losses[0]
+        output_dict.setdefault(OUTPUT_OPTIMIZATION_LOSSES, {})[LOSS_SEMSEG] = losses[0] * self._weight_semseg()
+        return losses[0]
+
+
+def compute_fg_loss(fg_logits, targets, output_dict):
+    """Mirror of TrainingModel.compute_fg_loss (model_builder.py:210-244): fg_logits [N,T,H,W]."""
+    gt, ignore = _one_sequence(fg_logits, targets)
+    losses = _SemsegLossFunction.apply(fg_logits[0], gt, ignore, 1)
+    output_dict.setdefault(OUTPUT_OPTIMIZATION_LOSSES, {})[LOSS_FOREGROUND] = losses[1]
+    return losses[1]

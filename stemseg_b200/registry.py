@@ -85,3 +85,11 @@ def install_into_reference(replace_default=True):
     import stemseg.modeling.model_builder as ref_builder
     ref_losses.EmbeddingLoss = EmbeddingLoss
     ref_builder.EmbeddingLoss = EmbeddingLoss
+    # semseg head losses: the registry entry build_model() looks up (model_builder.py:26,333-335) and the method the
+    # model calls for the foreground channel (model_builder.py:122,210-244)
+    from stemseg_b200.losses import CrossEntropyLoss, compute_fg_loss
+    ref_losses.CrossEntropyLoss = CrossEntropyLoss
+    ref_builder.CrossEntropyLoss = CrossEntropyLoss
+    ref_builder.SEMSEG_LOSS_REGISTRY._obj_map["CrossEntropy"] = CrossEntropyLoss
+    ref_builder.TrainingModel.compute_fg_loss = lambda self, fg_logits, targets, output_dict: compute_fg_loss(
+        fg_logits, targets, output_dict)

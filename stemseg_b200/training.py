@@ -128,11 +128,13 @@ def sgd_step(flat, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
 class DecoderTrainer(object):
     """forward -> loss -> backward -> gradient exchange -> SGD for the decoder heads, one sub-clip per rank per step.
 
-    heads: dict with 'embedding' (EmbeddingHead) and optionally 'seediness' (SeedinessHead), already on the device.
-    criterion: stemseg_b200.losses.EmbeddingLoss.  Hyper-parameters default to defaults.yaml:17-31."""
+    heads: dict with 'embedding' (EmbeddingHead) and optionally 'seediness' (SeedinessHead) and 'semseg' (SemsegHead,
+    YouTube-VIS / KITTI-MOTS configs: class cross-entropy + foreground BCE, csrc/semseg_loss.cu; targets then carry
+    'semseg_masks'), already on the device.  criterion: stemseg_b200.losses.EmbeddingLoss.  Hyper-parameters default to
+    defaults.yaml:17-34."""
 
     def __init__(self, heads, criterion, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True, group=None,
-                 use_graph=True, need_feature_grads=True, overlap_heads=True):
+                 use_graph=True, need_feature_grads=True, overlap_heads=True, weight_semseg=1.0):
         self.use_graph = use_graph
         # graph mode with two heads: run the heads' forward (and, after the loss, their backward) concurrently on two
         # streams inside ONE graph -- the latency-bound small kernels of one head hide under the tensor-core
@@ -143,9 +145,11 @@ class DecoderTrainer(object):
         self._graphs = {}
         self.embedding_head = heads["embedding"]
         self.seediness_head = heads.get("seediness")
+        self.semseg_head = heads.get("semseg")
+        self.weight_semseg = float(weight_semseg)            # cfg.TRAINING.LOSSES.WEIGHT_SEMSEG (defaults.yaml:34)
         self.criterion = criterion
         self.lr, self.momentum, self.weight_decay, self.nesterov = lr, momentum, weight_decay, nesterov
-        mods = [self.embedding_head] + ([self.seediness_head] if self.seediness_head is not None else [])
+        mods = self._modules()
         for m in mods:
             m.train()
         self.flats = [FlatParameters(m) for m in mods]
@@ -156,11 +160,19 @@ class DecoderTrainer(object):
                 dist.broadcast(flat.data, src=0, group=group)
 
     def forward_loss(self, feats_32_16_8_4, targets):
+        """TrainingModel.forward after the backbone (model_builder.py:107-126) through torch autograd."""
+        from stemseg_b200.losses import CrossEntropyLoss, compute_fg_loss
         out = self.embedding_head(feats_32_16_8_4)
         if self.seediness_head is not None:         # model_builder.py:198-201: cat(embedding head, seediness head)
             out = torch.cat((out, self.seediness_head(feats_32_16_8_4)), dim=1)
         output = {}
         loss = self.criterion(out, targets, output)
+        if self.semseg_head is not None:
+            logits = self.semseg_head(list(feats_32_16_8_4)[::-1]).permute(0, 2, 1, 3, 4)     # model_builder.py:179-180
+            if self.semseg_head.has_foreground_channel:
+                logits, fg_logits = logits.split((logits.shape[2] - 1, 1), dim=2)             # model_builder.py:121
+                loss = loss + compute_fg_loss(fg_logits.squeeze(2), targets, output)
+            loss = loss + CrossEntropyLoss(self.weight_semseg)(logits, targets, output) * self.weight_semseg
         return loss, output
 
     def step(self, feats_32_16_8_4, targets):
@@ -173,14 +185,14 @@ class DecoderTrainer(object):
         loss, output = self.forward_loss(feats_32_16_8_4, targets)
         loss.backward()
         self.exchange.finish()
-        for flat, mod in zip(self.flats, [self.embedding_head, self.seediness_head]):
+        for flat, mod in zip(self.flats, self._modules()):
             sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
             mod.invalidate_packed_weights()          # the kernel wrote the parameters behind autograd's back
         return output
 
     # ---- graph mode ---------------------------------------------------------------------------------------------
     def _modules(self):
-        return [self.embedding_head] + ([self.seediness_head] if self.seediness_head is not None else [])
+        return [m for m in (self.embedding_head, self.seediness_head, self.semseg_head) if m is not None]
 
     def _grad_slots(self, flat):
         names = {id(p): n for n, p in flat.module.named_parameters()}
@@ -227,44 +239,65 @@ class DecoderTrainer(object):
             for flat in flats:
                 sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
 
-        def seg_both_heads_concurrently():
+        def seg_heads_concurrently():
+            """Every head on its own stream: forward, join, losses + gradients on the main stream, fork, backward."""
+            from stemseg_b200.losses import semseg_loss_and_gradient
             main = torch.cuda.current_stream()
-            side = entry["side_stream"]
+            sides = entry["side_streams"][:len(mods) - 1]
+            streams = [main] + sides
 
             def fork():
                 ev = torch.cuda.Event()
                 ev.record(main)
-                side.wait_event(ev)
+                for st in sides:
+                    st.wait_event(ev)
 
             def join():
-                ev = torch.cuda.Event()
-                ev.record(side)
-                main.wait_event(ev)
+                for st in sides:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    main.wait_event(ev)
 
+            outs, saved = [None] * len(mods), [None] * len(mods)
             fork()
-            with torch.cuda.stream(side):                     # second head: forward on the side stream
-                mods[1].invalidate_packed_weights()
-                out1, sv1 = A.training_forward(mods[1], None, in_planes=entry["in_planes"])
-            mods[0].invalidate_packed_weights()
-            out0, sv0 = A.training_forward(mods[0], None, in_planes=entry["in_planes"])
+            for k in reversed(range(len(mods))):              # side streams first, the main-stream head last
+                with torch.cuda.stream(streams[k]):
+                    mods[k].invalidate_packed_weights()       # the repack kernels become part of the graph
+                    outs[k], saved[k] = A.training_forward(mods[k], None, in_planes=entry["in_planes"])
             join()
-            emb_map = torch.cat((out0, out1), dim=1)          # model_builder.py:198-201
+            n_emb = 2 if self.seediness_head is not None else 1
+            emb_map = outs[0] if n_emb == 1 else torch.cat((outs[0], outs[1]), dim=1)      # model_builder.py:198-201
             losses, grad = embedding_loss_and_gradient(emb_map, entry["masks"], entry["ignore"], self.criterion)
             entry["losses"] = losses
-            c0 = out0.shape[1]
-            state["grads_out"], state["saved"], state["outs"] = [grad[:, :c0], grad[:, c0:]], [sv0, sv1], [out0, out1]
+            c0 = outs[0].shape[1]
+            grads_out = [grad[:, :c0]] + ([grad[:, c0:]] if n_emb == 2 else [])
+            if self.semseg_head is not None:
+                sem = outs[-1]                                                           # [1, C, T, H, W]
+                g_sem = torch.empty_like(sem)
+                n_cls = sem.shape[1] - (1 if self.semseg_head.has_foreground_channel else 0)
+                cls_view = sem[0, :n_cls].permute(1, 0, 2, 3)                            # [T, cls, H, W] (model_builder.py:180)
+                fg = sem[0, n_cls] if self.semseg_head.has_foreground_channel else None
+                entry["semseg_losses"], _, _ = semseg_loss_and_gradient(
+                    cls_view, fg, entry["semseg_ids"], entry["ignore"], self.weight_semseg, 1.0, grad_out=g_sem[0])
+                grads_out.append(g_sem)
+            state["grads_out"], state["saved"], state["outs"] = grads_out, saved, outs
+            fgs = [None] * len(mods)
             fork()
-            with torch.cuda.stream(side):
-                fg1, _ = A.training_backward(mods[1], sv1, state["grads_out"][1], grad_dst=self._grad_slots(flats[1]),
-                                             need_feature_grads=self.need_feature_grads)
-            fg0, _ = A.training_backward(mods[0], sv0, state["grads_out"][0], grad_dst=self._grad_slots(flats[0]),
-                                         need_feature_grads=self.need_feature_grads)
+            for k in reversed(range(len(mods))):
+                with torch.cuda.stream(streams[k]):
+                    fgs[k], _ = A.training_backward(mods[k], saved[k], grads_out[k], grad_dst=self._grad_slots(flats[k]),
+                                                    need_feature_grads=self.need_feature_grads)
             join()
-            state["fg"] = (fg0, fg1)
-            entry["feature_grads"] = [a + b for a, b in zip(fg0, fg1)] if self.need_feature_grads else None
+            state["fg"] = fgs
+            total = None
+            if self.need_feature_grads:                       # every head reads the same pyramid
+                total = list(fgs[0])
+                for other in fgs[1:]:
+                    total = [a + b for a, b in zip(total, other)]
+            entry["feature_grads"] = total
 
-        if self.overlap_heads and len(mods) == 2:
-            return [seg_both_heads_concurrently, seg_optimizer]
+        if len(mods) >= 2 and (self.overlap_heads or self.semseg_head is not None):
+            return [seg_heads_concurrently, seg_optimizer]
         return [seg_forward_loss_backward_last, seg_backward_first, seg_optimizer]
 
     def _capture(self, feats, targets):
@@ -275,7 +308,9 @@ class DecoderTrainer(object):
         entry = {"in_planes": [D.pack_activation(f.detach(), planes) for f in feats],
                  "masks": masks.to(device=dev, dtype=torch.uint8).contiguous().clone(),
                  "ignore": targets[0]["ignore_masks"].to(device=dev, dtype=torch.uint8).contiguous().clone()}
-        entry["side_stream"] = torch.cuda.Stream(device=dev)
+        entry["side_streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        if self.semseg_head is not None:
+            entry["semseg_ids"] = targets[0]["semseg_masks"].to(device=dev, dtype=torch.int64).contiguous().clone()
         segments = self._segments(entry)
         # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, allocator) -- without the optimiser
         side = torch.cuda.Stream(device=dev)
@@ -316,6 +351,8 @@ class DecoderTrainer(object):
                 D.pack_activation(f.detach(), planes, out=pl)
             entry["masks"].copy_(masks, non_blocking=True)
             entry["ignore"].copy_(ignore, non_blocking=True)
+            if self.semseg_head is not None:
+                entry["semseg_ids"].copy_(targets[0]["semseg_masks"], non_blocking=True)
             pending = []
             graphs = entry["graphs"]
             if len(graphs) == 2:               # both heads in one graph, then both reductions
@@ -336,6 +373,13 @@ class DecoderTrainer(object):
             for m in self._modules():
                 m.invalidate_packed_weights()  # the packed copies inside the graph pool predate this step's update
         losses = entry["losses"]
-        return {"optimization_losses": {"embedding_loss": losses[0]},
-                "others": {"lovasz_loss": losses[1], "variance_smoothness_loss": losses[2], "seediness_loss": losses[3]},
-                "feature_grads": entry["feature_grads"]}
+        out = {"optimization_losses": {"embedding_loss": losses[0]},
+               "others": {"lovasz_loss": losses[1], "variance_smoothness_loss": losses[2], "seediness_loss": losses[3]},
+               "feature_grads": entry["feature_grads"]}
+        if self.semseg_head is not None:
+            sl = entry["semseg_losses"]
+            out["others"]["semantic_segmentation_loss"] = sl[0]
+            out["optimization_losses"]["semantic_segmentation_loss"] = sl[0] * self.weight_semseg
+            if self.semseg_head.has_foreground_channel:
+                out["optimization_losses"]["foreground"] = sl[1]
+        return out

@@ -38,3 +38,32 @@ def run_oracle(name, dtype=None):
         losses["total"].backward()
     grad = out.grad if out.grad is not None else torch.zeros_like(out)
     return {k: v.detach() for k, v in losses.items()}, grad
+
+
+def semseg_case_table():
+    c = {}
+    c["kitti_3cls_fg"] = dict(seed=31, t=4, h=24, w=32, num_classes=3)
+    c["ytvis_41cls_fg"] = dict(seed=32, t=2, h=16, w=24, num_classes=41)
+    c["five_cls_no_fg"] = dict(seed=33, t=4, h=12, w=20, num_classes=5, foreground_channel=False)
+    c["mostly_ignored"] = dict(seed=34, t=2, h=16, w=16, num_classes=4, ignore_frac=0.9)
+    c["ragged_8x30x50"] = dict(seed=35, t=8, h=30, w=50, num_classes=7, ignore_frac=0.0)
+    return c
+
+
+def build_semseg_case(name):
+    from oracle import loss_oracle as lo
+    return lo.seeded_semseg_case(**semseg_case_table()[name])
+
+
+def run_semseg_oracle(name, dtype=None):
+    """-> (loss dict, gradient of (semseg + foreground) wrt the head output [1,C,T,H,W])."""
+    from oracle import loss_oracle as lo
+    case = build_semseg_case(name)
+    out = case["out"].clone()
+    if dtype is not None:
+        out = out.to(dtype)
+    out.requires_grad_(True)
+    losses = lo.semseg_losses_sequence(out[0], case["semseg_masks"], case["ignore"], case["foreground_channel"])
+    total = losses["semseg"] if losses["foreground"] is None else losses["semseg"] + losses["foreground"]
+    total.backward()
+    return {k: (None if v is None else v.detach()) for k, v in losses.items()}, out.grad

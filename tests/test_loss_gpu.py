@@ -91,3 +91,68 @@ def test_rejects_cpu_and_batches(cuda_device):
         crit(two, [{"masks": case["masks"], "ignore_masks": case["ignore"]}] * 2, {})
     with pytest.raises(AssertionError):
         crit(case["out"][:, :3].to(cuda_device), [{"masks": case["masks"], "ignore_masks": case["ignore"]}], {})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# semantic-segmentation head losses (csrc/semseg_loss.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def semseg_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "semseg_loss_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(lc.semseg_case_table()))
+def test_semseg_losses_match_reference_fixture(name, semseg_golden, cuda_device):
+    """Fed exactly as TrainingModel.forward feeds the reference losses: permuted [N,T,C,H,W] view, foreground channel
+    split off (model_builder.py:119-124,180), two separate calls + backward through both."""
+    from stemseg_b200 import losses as L
+    case = lc.build_semseg_case(name)
+    out = case["out"].to(cuda_device).requires_grad_(True)
+    targets = [{"semseg_masks": case["semseg_masks"].to(cuda_device), "ignore_masks": case["ignore"].to(cuda_device)}]
+    logits = out.permute(0, 2, 1, 3, 4)
+    od = {}
+    total = 0
+    if case["foreground_channel"]:
+        logits, fg_logits = logits.split((logits.shape[2] - 1, 1), dim=2)
+        total = total + L.compute_fg_loss(fg_logits.squeeze(2), targets, od)
+    total = total + L.CrossEntropyLoss(1.0)(logits, targets, od)
+    total.backward()
+    torch.cuda.synchronize()
+    ref = float(semseg_golden["%s/semseg" % name])
+    assert abs(float(od[L.OUTPUT_OTHERS][L.LOSS_SEMSEG].detach()) - ref) <= LOSS_TOL * abs(ref)
+    if case["foreground_channel"]:
+        ref_fg = float(semseg_golden["%s/foreground" % name])
+        assert abs(float(od[L.OUTPUT_OPTIMIZATION_LOSSES][L.LOSS_FOREGROUND].detach()) - ref_fg) <= LOSS_TOL * abs(ref_fg)
+    ref_grad = torch.from_numpy(semseg_golden["%s/grad" % name])
+    assert float((out.grad.cpu() - ref_grad).norm() / ref_grad.norm()) <= GRAD_TOL
+
+
+def test_semseg_fused_call_and_weights(cuda_device):
+    """One call for both terms, writing into the head's gradient layout, with a non-unit class weight."""
+    from stemseg_b200.losses import semseg_loss_and_gradient
+    case = lc.build_semseg_case("ragged_8x30x50")
+    out = case["out"].to(cuda_device)
+    n_cls = out.shape[1] - 1
+    g = torch.empty_like(out)
+    losses, _, _ = semseg_loss_and_gradient(out[0, :n_cls].permute(1, 0, 2, 3), out[0, n_cls],
+                                            case["semseg_masks"].to(cuda_device), case["ignore"].to(cuda_device),
+                                            w_semseg=0.5, w_foreground=2.0, grad_out=g[0])
+    torch.cuda.synchronize()
+    o64 = case["out"].double().requires_grad_(True)
+    ref = lo.semseg_losses_sequence(o64[0], case["semseg_masks"], case["ignore"])
+    (0.5 * ref["semseg"] + 2.0 * ref["foreground"]).backward()
+    assert abs(float(losses[0]) - float(ref["semseg"])) <= LOSS_TOL * float(ref["semseg"])
+    assert abs(float(losses[1]) - float(ref["foreground"])) <= LOSS_TOL * float(ref["foreground"])
+    assert float((g.cpu().double() - o64.grad).norm() / o64.grad.norm()) <= GRAD_TOL
+
+
+def test_all_ignored_gives_nan_like_the_reference(cuda_device):
+    from stemseg_b200.losses import semseg_loss_and_gradient
+    case = lc.build_semseg_case("kitti_3cls_fg")
+    out = case["out"].to(cuda_device)
+    losses, _, _ = semseg_loss_and_gradient(out[0, :3].permute(1, 0, 2, 3), out[0, 3],
+                                            case["semseg_masks"].to(cuda_device),
+                                            torch.ones_like(case["ignore"]).to(cuda_device))
+    ref = lo.semseg_losses_sequence(case["out"][0], case["semseg_masks"], torch.ones_like(case["ignore"]))
+    assert torch.isnan(ref["semseg"]) and torch.isnan(ref["foreground"])
+    assert torch.isnan(losses).all()

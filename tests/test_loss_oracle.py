@@ -48,3 +48,31 @@ def test_empty_first_instance_shifts_targets(golden):
     aligned = lo.loss_from_head_output(case["out"], case["masks"][1:], case["ignore"], case["embedding_size"],
                                        case["n_free"], lc.FREE_DIM_STDS[case["n_free"]], **lc.WEIGHTS)
     assert abs(float(aligned["lovasz"]) - float(golden["empty_first/lovasz"])) > 1e-3
+
+
+@pytest.fixture(scope="module")
+def semseg_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "semseg_loss_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(lc.semseg_case_table()))
+def test_semseg_oracle_reproduces_reference(name, semseg_golden):
+    losses, grad = lc.run_semseg_oracle(name)
+    for key in ("semseg", "foreground"):
+        if losses[key] is None:
+            assert "%s/%s" % (name, key) not in semseg_golden
+            continue
+        ref = float(semseg_golden["%s/%s" % (name, key)])
+        assert abs(float(losses[key]) - ref) <= 1e-6 * max(abs(ref), 1e-3)
+    ref_grad = torch.from_numpy(semseg_golden["%s/grad" % name])
+    assert float((grad - ref_grad).norm() / ref_grad.norm()) <= 1e-5
+
+
+def test_ignore_mask_does_not_touch_the_class_loss():
+    """Quirk: F.cross_entropy's default mean reduction makes the ignore mask cancel out of the class loss."""
+    from oracle import loss_oracle as lo
+    case = lc.build_semseg_case("kitti_3cls_fg")
+    a = lo.semseg_losses_sequence(case["out"][0], case["semseg_masks"], case["ignore"])
+    b = lo.semseg_losses_sequence(case["out"][0], case["semseg_masks"], torch.zeros_like(case["ignore"]))
+    assert abs(float(a["semseg"]) - float(b["semseg"])) <= 1e-6 * float(a["semseg"])
+    assert abs(float(a["foreground"]) - float(b["foreground"])) > 1e-4

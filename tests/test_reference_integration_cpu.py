@@ -44,6 +44,9 @@ def test_install_into_reference_and_strict_state_dict():
                                      nbr_free_dims=len(cfg.TRAINING.LOSSES.EMBEDDING.FREE_DIM_STDS),
                                      **cfg.TRAINING.LOSSES.EMBEDDING.d())
     assert crit.num_input_channels == 2 * cfg.MODEL.EMBEDDINGS.EMBEDDING_SIZE - crit.n_free_dims + 1
+    from stemseg_b200.losses import CrossEntropyLoss
+    assert ref_builder.SEMSEG_LOSS_REGISTRY[cfg.TRAINING.LOSSES.SEMSEG] is CrossEntropyLoss     # model_builder.py:334
+    assert ref_builder.TrainingModel.compute_fg_loss.__name__ == "<lambda>"
 
 
 def test_same_seed_gives_identical_init():

@@ -150,3 +150,57 @@ def test_graph_steps_track_the_autograd_steps(cuda_device):
         for a, g in zip(l_a, l_g):
             assert abs(a - g) <= 1e-5 * abs(a)
         assert float((p_a - p_g).norm() / p_a.norm()) <= 1e-6
+
+
+def test_semseg_config_trainer_step(cuda_device):
+    """YouTube-VIS / KITTI-MOTS wiring: embedding head with its own seediness channel + semseg head with a foreground
+    channel.  The CUDA-graph step (three... two heads on two streams) and the autograd step must produce the same
+    losses and the same parameter update; the losses must match the float64 oracles."""
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    from stemseg_b200.losses import EmbeddingLoss
+    from stemseg_b200.training import DecoderTrainer
+    t, h4, w4 = 4, 24, 32
+    feats = do.seeded_features(703, 1, 32, t, h4, w4)
+    case = lo.seeded_case(seed=704, t=t, h=h4, w=w4, embedding_size=4, n_free=2, instances=2)
+    sem_case = lo.seeded_semseg_case(seed=705, t=t, h=h4, w=w4, num_classes=5)
+    emb_sd = do.seeded_state_dict(do.head_parameter_shapes("embedding", 32, [32] * 4, embedding_size=4, dim_mode="xyff",
+                                                           seediness_output=True), 706)
+    sem_sd = do.seeded_state_dict(do.head_parameter_shapes("semseg", 32, [64] * 4, num_out=6), 707)
+    norm = lambda c: nn.GroupNorm(32, c)       # noqa: E731
+    results = []
+    for use_graph in (False, True):
+        emb = heads.EmbeddingHead(32, [32] * 4, 4, True, True, "xyff", NormType=norm, num_frames=t).to(cuda_device)
+        sem = heads.SemsegHead(32, 5, [64] * 4, (4, 8, 16, 32), foreground_channel=True, NormType=norm,
+                               num_frames=t).to(cuda_device)
+        emb.load_state_dict(emb_sd, strict=True)
+        sem.load_state_dict(sem_sd, strict=True)
+        crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3],
+                             weight_variance_smoothness=10.0, weight_lovasz=1.0, weight_regularization=0.001,
+                             weight_seediness=1.0, weight=1.0)
+        trainer = DecoderTrainer({"embedding": emb, "semseg": sem}, crit, lr=0.05, use_graph=use_graph,
+                                 weight_semseg=0.7)
+        targets = [{"masks": case["masks"].to(cuda_device), "ignore_masks": case["ignore"].to(cuda_device),
+                    "semseg_masks": sem_case["semseg_masks"].to(cuda_device)}]
+        fdev = [f.to(cuda_device).requires_grad_(True) for f in feats]
+        out = trainer.step(fdev, targets)
+        torch.cuda.synchronize()
+        ol = out["optimization_losses"]
+        results.append(({k: float(v.detach()) for k, v in ol.items()},
+                        torch.cat([f.data.clone() for f in trainer.flats]).cpu()))
+    (l_a, p_a), (l_g, p_g) = results
+    assert set(l_a) == set(l_g) == {"embedding_loss", "semantic_segmentation_loss", "foreground"}
+    for k in l_a:
+        assert abs(l_a[k] - l_g[k]) <= 1e-5 * abs(l_a[k]), k
+    assert float((p_a - p_g).norm() / p_a.norm()) <= 1e-6
+    # losses against the float64 oracles on the oracle's own forward (tolerance of the fp32-parity forward)
+    e64 = {k: v.double() for k, v in emb_sd.items()}
+    s64 = {k: v.double() for k, v in sem_sd.items()}
+    f64 = [f.double() for f in feats]
+    emb_out = do.embedding_head(e64, f64, t, 4, "xyff", True, True)
+    sem_out = do.semseg_head(s64, f64[::-1], t)
+    ref_e = lo.loss_from_head_output(emb_out, case["masks"], case["ignore"], 4, 2, [0.3, 0.3], **lc.WEIGHTS)
+    ref_s = lo.semseg_losses_sequence(sem_out[0], sem_case["semseg_masks"], case["ignore"])
+    assert abs(l_g["embedding_loss"] - float(ref_e["total"])) <= 2e-4 * abs(float(ref_e["total"]))
+    assert abs(l_g["semantic_segmentation_loss"] - 0.7 * float(ref_s["semseg"])) <= 2e-4 * float(ref_s["semseg"])
+    assert abs(l_g["foreground"] - float(ref_s["foreground"])) <= 2e-4 * float(ref_s["foreground"])
