@@ -217,3 +217,25 @@ def ptr(t):
 def stream_ptr():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class capture_guard(object):
+    """Keeps Python's cyclic garbage collector out of a CUDA-graph capture.
+
+    Objects that own CUDA graphs (an older pipeline / trainer that became garbage) are destroyed whenever the cyclic
+    collector happens to run; destroying a graph while ANOTHER stream capture is in progress invalidates that capture
+    ("operation not permitted when stream is capturing").  torch.cuda.graph no longer forces a collection on entry, so
+    collect up front and hold the collector off until the capture is over."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self._was_enabled = gc.isenabled()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was_enabled:
+            gc.enable()
+        return False

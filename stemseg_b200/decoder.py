@@ -492,7 +492,7 @@ class HeadSet(object):
         streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]     # small branches: high priority
         KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]
-        with torch.cuda.graph(graph):
+        with _lib.capture_guard(), torch.cuda.graph(graph):
             outputs = self._plan(in_planes, streams=streams)
         kernels = _lib.KERNEL_LAUNCHES[0] - before
         keep, KEEP = KEEP, []

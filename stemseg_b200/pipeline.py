@@ -182,7 +182,7 @@ class SubclipPipeline(object):
         from stemseg_b200 import _lib
         D.KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]
-        with torch.cuda.graph(graph):
+        with _lib.capture_guard(), torch.cuda.graph(graph):
             state = body(streams)
         kernels = _lib.KERNEL_LAUNCHES[0] - before
         keep, D.KEEP = D.KEEP, []

@@ -321,13 +321,14 @@ class DecoderTrainer(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graphs, pool = [], None
-        for seg in segments:
-            g = torch.cuda.CUDAGraph()
-            before = _lib.KERNEL_LAUNCHES[0]
-            with torch.cuda.graph(g, pool=pool):
-                seg()
-            pool = g.pool()
-            graphs.append((g, _lib.KERNEL_LAUNCHES[0] - before))
+        with _lib.capture_guard():
+            for seg in segments:
+                g = torch.cuda.CUDAGraph()
+                before = _lib.KERNEL_LAUNCHES[0]
+                with torch.cuda.graph(g, pool=pool):
+                    seg()
+                pool = g.pool()
+                graphs.append((g, _lib.KERNEL_LAUNCHES[0] - before))
         entry["graphs"] = graphs
         entry["segments"] = segments           # keeps every captured buffer alive
         for flat in self.flats:                # the captures ran nothing: gradients / momentum are still untouched
