@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) gn_backward_apply_kernel(float* __restric
 // bias gradient).  dy is never materialised in fp32: one read of dn and y, one 4-byte-per-element write, instead of
 // apply (read 8 B, write 4 B) + channel sum (read 4 B) + plane conversion (read 4 B, write 4 B).
 // Block = one chunk of kApChunk voxels; bias partials [chunks][c] are reduced in a fixed order afterwards.
-constexpr int kApChunk = 256;
+constexpr int kApChunk = 64;
 
 __global__ void __launch_bounds__(256) gn_backward_apply_planes_kernel(
     const float* __restrict__ dn, const float* __restrict__ y, const float* __restrict__ mean_rstd,
@@ -459,12 +459,31 @@ __global__ void __launch_bounds__(256) gn_backward_apply_planes_kernel(
     const long long v0 = 1ll * blockIdx.x * kApChunk;
     long long v1 = v0 + kApChunk;
     if (v1 > rows_total) v1 = rows_total;
-    float g4[4];
+    // per-channel constants of dy = rstd (gamma dn - A - x_hat B) = a1 dn + a2 y + a3 are hoisted out of the voxel loop
+    // whenever the chunk lies inside one sample (always for batch 1)
+    const int n_first = static_cast<int>(v0 / spatial);
+    const bool one_sample = (v1 - 1) / spatial == n_first;
+    float g4[4], mu[4], rs[4], ga[4], gb[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) g4[k] = gamma[4 * q + k];
+    for (int k = 0; k < 4; ++k) {
+        const int ch = 4 * q + k, g = ch / cpg;
+        g4[k] = gamma[ch];
+        const float* mr = mean_rstd + (static_cast<size_t>(n_first) * groups + g) * 2;
+        const float* gt = group_terms + (static_cast<size_t>(n_first) * groups + g) * 2;
+        mu[k] = mr[0]; rs[k] = mr[1]; ga[k] = gt[0]; gb[k] = gt[1];
+    }
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long v = v0 + r; v < v1; v += rows) {
-        const int nn = static_cast<int>(v / spatial);
+        if (!one_sample) {
+            const int nn = static_cast<int>(v / spatial);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int g = (4 * q + k) / cpg;
+                const float* mr = mean_rstd + (static_cast<size_t>(nn) * groups + g) * 2;
+                const float* gt = group_terms + (static_cast<size_t>(nn) * groups + g) * 2;
+                mu[k] = mr[0]; rs[k] = mr[1]; ga[k] = gt[0]; gb[k] = gt[1];
+            }
+        }
         const long long i = v * quads + q;
         const float4 d = __ldg(reinterpret_cast<const float4*>(dn) + i);
         const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + i);
@@ -473,11 +492,8 @@ __global__ void __launch_bounds__(256) gn_backward_apply_planes_kernel(
         __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int g = (4 * q + k) / cpg;
-            const float* mr = mean_rstd + (static_cast<size_t>(nn) * groups + g) * 2;
-            const float* gt = group_terms + (static_cast<size_t>(nn) * groups + g) * 2;
-            const float xh = (yv[k] - mr[0]) * mr[1];
-            const float o = mr[1] * (g4[k] * dv[k] - gt[0] - xh * gt[1]);      // same expression as gn_backward_apply
+            const float xh = (yv[k] - mu[k]) * rs[k];
+            const float o = rs[k] * (g4[k] * dv[k] - ga[k] - xh * gb[k]);       // same expression as gn_backward_apply
             s[k] += o;
             split_bf16_b(o, hi[k], lo[k]);
         }
