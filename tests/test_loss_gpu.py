@@ -156,3 +156,25 @@ def test_all_ignored_gives_nan_like_the_reference(cuda_device):
     ref = lo.semseg_losses_sequence(case["out"][0], case["semseg_masks"], torch.ones_like(case["ignore"]))
     assert torch.isnan(ref["semseg"]) and torch.isnan(ref["foreground"])
     assert torch.isnan(losses).all()
+
+
+def test_maximum_instance_count(cuda_device):
+    """STEMSEG_MAX_LOSS_INSTANCES (32) instances in one clip (thin stripes, every second one empty -> the kept slots are
+    scored against shifted targets, quirk (i)); one more raises."""
+    from stemseg_b200 import _lib
+    t, h, w, n_inst = 2, 16, 64, _lib.STEMSEG_MAX_LOSS_INSTANCES
+    case = lo.seeded_case(seed=77, t=t, h=h, w=w, embedding_size=4, n_free=2, instances=1)
+    masks = torch.zeros(n_inst, t, h, w, dtype=torch.uint8)
+    for i in range(0, n_inst, 2):
+        masks[i, :, :, 2 * i:2 * i + 3] = 1
+    case["masks"] = masks
+    got, grad = _run_cuda(case, cuda_device)
+    out64 = case["out"].double().requires_grad_(True)
+    ref = lo.loss_from_head_output(out64, masks, case["ignore"], 4, 2, lc.FREE_DIM_STDS[2], **lc.WEIGHTS)
+    ref["total"].backward()
+    for key, val in got.items():
+        assert abs(val - float(ref[key])) <= LOSS_TOL * max(abs(float(ref[key])), 1e-3), (key, val, float(ref[key]))
+    assert float((grad.double() - out64.grad).norm() / out64.grad.norm()) <= GRAD_TOL
+    case["masks"] = torch.zeros(n_inst + 1, t, h, w, dtype=torch.uint8)
+    with pytest.raises(ValueError):
+        _run_cuda(case, cuda_device)
