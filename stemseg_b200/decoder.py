@@ -358,21 +358,40 @@ class HeadSet(object):
         self.fuse_stats = True              # GroupNorm statistics from the conv epilogue (unsplit layers)
         self.chunk_long_layers = True       # long layers as short-lived CTAs + high-priority side branches
         self.pools, self.tscale = pool_schedule(num_frames)
+        # first conv of every block: heads are fused along the GEMM N dimension in GROUPS whose total width keeps the
+        # widest N tile (a multiple of 256, or anything up to 256); e.g. embedding (128) + semseg (256) = 384 would fall
+        # back to three N=128 tiles, so those two run as separate launches (N=256 and N=128) instead
         self.first_stage = {}
         for name, _ in BLOCKS:
-            self.first_stage[name] = _fuse_rows([s.weights.stages[name][0][0] for s in self.specs])
+            convs = [s.weights.stages[name][0][0] for s in self.specs]
+            total = sum(c.cout for c in convs)
+            if total <= 256 or total % 256 == 0:
+                groups = [list(range(len(convs)))]
+            else:
+                wide = [i for i, c in enumerate(convs) if c.cout % 256 == 0]
+                rest = [i for i in range(len(convs)) if i not in wide]
+                rest_total = sum(convs[i].cout for i in rest)
+                rest_groups = [rest] if (rest_total <= 256 or rest_total % 256 == 0) else [[i] for i in rest]
+                groups = ([wide] if wide else []) + [g for g in rest_groups if g]
+            self.first_stage[name] = [(_fuse_rows([convs[i] for i in g]), g) for g in groups]
         self._entries = {}
 
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
     def _branch(self, name, n_stages, a_in, trace):
         """All conv stages of one scale block for every head; returns per-head Planes."""
-        res = conv3d(a_in, self.first_stage[name], allow_split=True, want_stats=self.fuse_stats,
-                     chunked=self.chunk_long_layers)
-        y, stat = res if self.fuse_stats else (res, None)
-        KEEP.extend((y, stat))
-        outs, c0 = [], 0
+        first = {}                                   # head index -> (conv output, statistics, channel offset)
+        for fused, members in self.first_stage[name]:
+            res = conv3d(a_in, fused, allow_split=True, want_stats=self.fuse_stats, chunked=self.chunk_long_layers)
+            y, stat = res if self.fuse_stats else (res, None)
+            KEEP.extend((y, stat))
+            c0 = 0
+            for hi in members:
+                first[hi] = (y, stat, c0)
+                c0 += self.specs[hi].weights.stages[name][0][0].cout
+        outs = []
         for hi, spec in enumerate(self.specs):
             conv, gamma, beta = spec.weights.stages[name][0]
+            y, stat, c0 = first[hi]
             if trace is not None and hi == trace[0]:
                 full = y.sum(0) if y.dim() == 6 else y.clone()
                 trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
@@ -380,7 +399,6 @@ class HeadSet(object):
                                      self.pools[0] and name != "block_4x", self.planes,
                                      channel_slice=(c0, conv.cout), stat=stat)
             KEEP.append(a.tensor)
-            c0 += conv.cout
             for j in range(1, n_stages):
                 conv, gamma, beta = spec.weights.stages[name][j]
                 res = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats)

@@ -30,13 +30,19 @@ def _oracle_heads(pipe, feats_list, t):
     return out[:e.embedding_size], out[e.embedding_size:ev], seed, semseg
 
 
-@pytest.mark.parametrize("config", ["davis", "youtube_vis", "kitti_mots"])
-def test_shipped_config_pipeline(config, cuda_device):
+# (config, semseg widths): embedding 32 + semseg 256 = 288 output channels in the fused first-stage GEMM exercises the
+# grouped launches (N=256 for the semseg head, N=32 for the embedding head) that production YouTube-VIS widths take
+@pytest.mark.parametrize("config,semseg_widths", [("davis", 64), ("youtube_vis", 64), ("kitti_mots", 64),
+                                                  ("youtube_vis", 256)])
+def test_shipped_config_pipeline(config, semseg_widths, cuda_device):
     from stemseg_b200.foreground import gather_points
     from stemseg_b200.pipeline import build_pipeline
     t, h4, w4 = 8, 24, 32
     pipe = build_pipeline(config, cuda_device, num_frames=t, in_channels=32, inter_channels=(32, 32, 32, 32),
-                          semseg_inter_channels=(64, 64, 64, 64), num_classes=5, min_seediness_prob=0.0)
+                          semseg_inter_channels=(semseg_widths,) * 4, num_classes=5, min_seediness_prob=0.0)
+    if pipe.semseg_head is not None:
+        n_groups = len(pipe._head_group().first_stage["block_4x"])
+        assert n_groups == (2 if semseg_widths == 256 else 1)
     feats_list = do.seeded_features(900 + len(config), 1, 32, t, h4, w4)
     feats = {s: f.to(cuda_device) for s, f in zip((32, 16, 8, 4), feats_list)}
     if pipe.semseg_head is None:
