@@ -332,6 +332,20 @@ def _fuse_rows(convs):
     return PackedConv(planes_tensor, bias, first.cin, sum(c.cout for c in convs), first.kernel_size)
 
 
+def first_stage_groups(couts):
+    """Which heads share one first-stage GEMM: lists of head indices.  One group when the concatenated width keeps
+    the widest N tile (<= 256 or a multiple of 256); otherwise the heads whose own width is a multiple of 256 form
+    one group and the rest another (or one launch each if their sum still does not tile)."""
+    total = sum(couts)
+    if total <= 256 or total % 256 == 0:
+        return [list(range(len(couts)))]
+    wide = [i for i, c in enumerate(couts) if c % 256 == 0]
+    rest = [i for i in range(len(couts)) if i not in wide]
+    rest_total = sum(couts[i] for i in rest)
+    rest_groups = [rest] if (rest_total <= 256 or rest_total % 256 == 0) else [[i] for i in rest]
+    return ([wide] if wide else []) + [g for g in rest_groups if g]
+
+
 # intermediates of the plan currently being built / captured: kept alive so that no buffer is recycled while a
 # parallel branch of the CUDA graph may still read it
 KEEP = []
@@ -364,15 +378,7 @@ class HeadSet(object):
         self.first_stage = {}
         for name, _ in BLOCKS:
             convs = [s.weights.stages[name][0][0] for s in self.specs]
-            total = sum(c.cout for c in convs)
-            if total <= 256 or total % 256 == 0:
-                groups = [list(range(len(convs)))]
-            else:
-                wide = [i for i, c in enumerate(convs) if c.cout % 256 == 0]
-                rest = [i for i in range(len(convs)) if i not in wide]
-                rest_total = sum(convs[i].cout for i in rest)
-                rest_groups = [rest] if (rest_total <= 256 or rest_total % 256 == 0) else [[i] for i in rest]
-                groups = ([wide] if wide else []) + [g for g in rest_groups if g]
+            groups = first_stage_groups([c.cout for c in convs])
             self.first_stage[name] = [(_fuse_rows([convs[i] for i in g]), g) for g in groups]
         self._entries = {}
 

@@ -62,3 +62,17 @@ def test_cpu_device_is_rejected():
     from stemseg_b200.clusterers import SequentialClustering
     with pytest.raises(ValueError):
         SequentialClustering(0.5, 0.3, 0.8, 2, [0.3, 0.3], "cpu")
+
+
+def test_first_stage_grouping_rule():
+    """Host logic of the launch plan: which heads share one first-stage GEMM (stemseg_b200/decoder.py)."""
+    from stemseg_b200.decoder import first_stage_groups
+    assert first_stage_groups([128, 128]) == [[0, 1]]                 # DAVIS 4x / 8x: N = 256
+    assert first_stage_groups([256, 256]) == [[0, 1]]                 # every config at 32x / 16x: N = 512 -> 2 x 256
+    assert first_stage_groups([128, 256]) == [[1], [0]]               # YouTube-VIS 4x / 8x: 384 would need N = 128 tiles
+    assert first_stage_groups([128, 128, 256]) == [[0, 1, 2]]         # three heads, 512
+    assert first_stage_groups([32, 64]) == [[0, 1]]                   # small test widths stay fused
+    assert first_stage_groups([96, 96, 96]) == [[0], [1], [2]]
+    for couts in ([128, 256, 256], [64], [256, 128, 128, 256]):
+        flat = sorted(i for g in first_stage_groups(couts) for i in g)
+        assert flat == list(range(len(couts)))
