@@ -29,9 +29,10 @@ def _digest():
     h.update(" ".join(NVCC_FLAGS).encode())
     inc = os.path.join(os.path.dirname(PKG_DIR), "include", "stemseg_b200.h")
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    root = os.path.dirname(PKG_DIR)
     for path in files + [inc]:
         with open(path, "rb") as f:
-            h.update(path.encode())
+            h.update(os.path.relpath(path, root).encode())        # checkout-location independent
             h.update(f.read())
     return h.hexdigest()
 

@@ -330,6 +330,7 @@ def stitch_subsequences_device(num_frames, subseq_frames, subseq_labels, subseq_
         lut_local = [l + offset for l in range(1, k + 2)]           # local label l -> global label (index l - 1)
         if i == 0:
             per_frame_h = per_frame.cpu().numpy()
+            assert int(bad0.item()) == 0, "label outside the histogram range"
             _relabel(labels, 1, lut_local)
             for j, t in enumerate(frames):
                 frame_labels[t] = labels[starts[j]:starts[j + 1]]
@@ -340,6 +341,9 @@ def stitch_subsequences_device(num_frames, subseq_frames, subseq_labels, subseq_
             overlapping = sorted(list(overlap_set))
             existing = torch.cat([frame_labels[t] for t in overlapping])
             current = torch.cat([labels[starts[j]:starts[j + 1]] for j, t in enumerate(frames) if t in overlap_set])
+            assert existing.numel() == current.numel(), \
+                "Shape mismatch: {}, {} (overlap frames must hold the same foreground points in both sub-clips)".format(
+                    tuple(existing.shape), tuple(current.shape))
             na = next_track_label + 1
             joint, bad1 = _pair_histogram(existing, current, 1, 1, na, k + 2)
             joint_h = joint.cpu().numpy().astype(np.int64)           # sync: the small tables

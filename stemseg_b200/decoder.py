@@ -92,7 +92,11 @@ def pack_activation(x, planes, out=None):
         raise ValueError("decoder inputs must be fp32 CUDA tensors (got %s on %s); there is no CPU path" % (
             x.dtype, x.device))
     n, c, t, h, w = x.shape
-    if not (x.stride(4) == 1 and x.stride(3) == w):
+    # channels-last producer (a torch backbone run in channels_last emits [T,C,H,W] tensors whose memory is already
+    # T,H,W,C): the NCTHW view of it IS the NDHWC layout of the planes, so D0 degenerates to the elementwise split
+    ndhwc = (c > 1 and x.stride(1) == 1 and x.stride(4) == c and x.stride(3) == w * c and x.stride(2) == h * w * c
+             and (n == 1 or x.stride(0) == t * h * w * c) and (n * c * t * h * w) % 4 == 0 and x.data_ptr() % 16 == 0)
+    if not ndhwc and not (x.stride(4) == 1 and x.stride(3) == w):
         x = x.contiguous()
     with torch.cuda.device(x.device):
         if out is not None:
@@ -102,8 +106,11 @@ def pack_activation(x, planes, out=None):
             dst = out.tensor
         else:
             dst = torch.empty((planes, n, t, h, w, c), dtype=torch.bfloat16, device=x.device)
-        _check(lib.stemseg_pack_activation(_lib.ptr(x), x.stride(0), x.stride(1), x.stride(2), n, c, t, h * w,
-                                           _lib.ptr(dst), planes, _lib.stream_ptr()))
+        if ndhwc:
+            _check(lib.stemseg_to_planes(_lib.ptr(x), n * c * t * h * w, _lib.ptr(dst), planes, _lib.stream_ptr()))
+        else:
+            _check(lib.stemseg_pack_activation(_lib.ptr(x), x.stride(0), x.stride(1), x.stride(2), n, c, t, h * w,
+                                               _lib.ptr(dst), planes, _lib.stream_ptr()))
     return Planes(dst, n, t, h, w, c)
 
 

@@ -129,10 +129,17 @@ def exchange_and_stitch_device(num_frames, subseq_frames, local_results, group=N
 def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, group=None):
     """Run the owned sub-clips through ``pipeline`` (stemseg_b200.pipeline.SubclipPipeline) and stitch globally.
 
-    masks: [T,h,w] foreground masks of the whole video (or None -> per-sub-clip seediness threshold);
+    masks: [T,h,w] foreground masks of the whole video (None is only accepted for a single sub-clip: per-sub-clip
+    seediness thresholds would give overlap frames different point sets in different sub-clips);
     features_for_clip(i) -> {scale: tensor} pyramid of sub-clip i (only called for owned sub-clips)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if masks is None and len(subseq_frames) > 1:
+        # a per-sub-clip seediness threshold gives overlap frames a different point set in each sub-clip; the stitch
+        # needs identical points there (the reference averages seediness / semseg per frame over all sub-clips first,
+        # inference/main.py:93-103) -> build the video masks with FrameAverager.foreground_index and pass them in
+        raise ValueError("clip_parallel_process needs the video's foreground masks when there is more than one "
+                         "sub-clip (build them with stemseg_b200.foreground.FrameAverager)")
     local = {}
 
     def collect(i, pend):
