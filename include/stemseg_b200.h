@@ -255,12 +255,40 @@ int32_t stemseg_conv1x1_head_output(const void* act_planes, const void* weight_p
  *            the per-frame unique / count loops of get_track_mask_idxes         online_chainer.py:94-117
  * table[ia][ib] counts the points with bin(a) == ia and bin(b) == ib, where bin(v) = 0 for v < 0 (outliers) and
  * v - base + 1 otherwise; values outside the table increment *out_of_range (caller error).  Intersection, sizes and
- * unions of every label pair follow from this one table; the Hungarian solve stays on the host.
+ * unions of every label pair follow from this one table (host-side Hungarian: stemseg_b200.chaining.
+ * stitch_subsequences_device; fully device-resident: stemseg_stitch_subclip below).
  * ---------------------------------------------------------------------------------------------------------- */
 int32_t stemseg_label_pair_histogram(const int64_t* a, const int64_t* b, int64_t n, int64_t a_base, int64_t b_base,
                                      int32_t na, int32_t nb, int32_t* table, int32_t* out_of_range, void* stream);
 /* labels[i] = lut[labels[i] - base] for labels[i] >= base (negative labels and labels outside the table unchanged) */
 int32_t stemseg_relabel_lut(int64_t* labels, int64_t n, int64_t base, const int64_t* lut, int32_t nlut, void* stream);
+
+/* The whole sequential stitch of one sub-clip, resident on the device (no host round trip per sub-clip):
+ *   replaces OnlineChainer.process for sub-clip i (online_chainer.py:162-236): TrackContainer.add_labels / get_labels,
+ *            associate_clusters incl. scipy.optimize.linear_sum_assignment (online_chainer.py:291-343, :330),
+ *            the relabelling of the non-overlap frames (:213-224), the meta-info update (:227-229) and the statistics
+ *            of TrackContainer.get_track_mask_idxes (:94-117).
+ * labels        [capacity] LOCAL labels of the sub-clip (clustered with cluster_label_start = 1; -1 = outlier), frames
+ *               concatenated; rewritten in place to the labels OnlineChainer.process returns in subseq_labels_list
+ *               (overlap frames: local + next_track_label - 1; other frames: associated track ids).
+ * frame_counts  DEVICE int32 [n_frames] points per frame;  k_dev  DEVICE int32: number of clusters of the sub-clip.
+ * frames / overlap  HOST int32 [n_frames]: global frame number of each slot, and 1 if that frame is shared with the
+ *               previous sub-clip (already in the container).  is_first: sub-clip 0 (no association).
+ * container     frame_labels int64 [num_frames][frame_capacity], frame_count int32 [num_frames] (-1 = absent).
+ * state         int32 [4]: next_track_label (init 1), highest id (init 0), error flags (init 0), sub-clips done.
+ * track_counts  int64 [max_labels + 1] (index = id + 1: slot 0 counts the outliers), span_lo / span_hi int32
+ *               [max_labels + 1] first / last frame of every id (init 10000 / -1 like online_chainer.py:97).
+ * meta_labels_out  DEVICE int64 [max_instances]: instance_labels of the sub-clip after association (-1 padding).
+ * Error flags (state[2]): 1 label outside range, 2 overlap frames differ in size, 4 label sets overlap, 8 too many
+ * labels, 16 frame already present, 32 assignment failed.  The label lists are ordered like CPython's
+ * list(set(...) - {-1}) and the assignment is scipy's algorithm, so ties resolve exactly as in the reference. */
+size_t stemseg_stitch_workspace_bytes(int32_t max_instances, int32_t n_frames, int32_t max_labels);
+int32_t stemseg_stitch_subclip(int64_t* labels, int64_t capacity, const int32_t* frame_counts, const int32_t* k_dev,
+                               const int32_t* frames, const int32_t* overlap, int32_t n_frames, int32_t is_first,
+                               int32_t max_instances, int64_t* frame_labels, int32_t* frame_count,
+                               int64_t frame_capacity, int32_t num_frames, int32_t* state, int64_t* track_counts,
+                               int32_t* span_lo, int32_t* span_hi, int32_t max_labels, int64_t* meta_labels_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Instance-mask writeback

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -58,6 +58,10 @@ PROTOTYPES = {
     "stemseg_label_pair_histogram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                                c_void_p, c_void_p, c_void_p]),
     "stemseg_relabel_lut": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "stemseg_stitch_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "stemseg_stitch_subclip": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                         c_int32, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_rank_map_scatter": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "stemseg_mask_writeback": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_void_p, c_void_p]),
@@ -150,7 +154,7 @@ KERNELS_PER_CALL = {
     "stemseg_pack_activation": 1, "stemseg_pack_conv_weight": 1, "stemseg_conv3d_bf16_planes": 1,
     "stemseg_group_norm_stats": 2, "stemseg_group_norm_finalize": 1, "stemseg_norm_relu_pool": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
     "stemseg_head_lowres": 1, "stemseg_conv1x1_head_output": 1,
-    "stemseg_label_pair_histogram": 1, "stemseg_relabel_lut": 1,
+    "stemseg_label_pair_histogram": 1, "stemseg_relabel_lut": 1, "stemseg_stitch_subclip": 3,
     "stemseg_rank_map_scatter": 1, "stemseg_mask_writeback": 1,
     "stemseg_pack_conv_weight_dgrad": 1, "stemseg_head_backward": 3, "stemseg_upsample_transpose": 1,
     "stemseg_pool_relu_backward": 1, "stemseg_group_norm_backward": 3, "stemseg_channel_sum": 2,

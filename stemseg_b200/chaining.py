@@ -388,3 +388,134 @@ def stitch_subsequences_device(num_frames, subseq_frames, subseq_labels, subseq_
         out_labels.append(labels)
         out_meta.append(meta)
     return DeviceTrackContainer(frame_labels, counts, spans), out_labels, out_meta
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fully device-resident stitch: nothing is read back per sub-clip (csrc/stitch.cu: stemseg_stitch_subclip)
+# ----------------------------------------------------------------------------------------------------------------
+STITCH_ERRORS = {1: "label outside the expected range", 2: "Shape mismatch: overlap frames hold different point sets",
+                 4: "Labels overlap", 8: "too many labels for the stitch tables", 16: "frame labels already exist",
+                 32: "assignment failed"}
+
+
+class DeviceStitcher(object):
+    """``OnlineChainer.process``'s sequential stitch (online_chainer.py:162-236) as three kernel launches per sub-clip
+    and ONE device->host copy per video.
+
+    The track container (per-frame label vectors, highest id, per-id point counts / lifetimes), the label association
+    (IoU table -> scipy-identical assignment, csrc/assoc.cuh) and ``next_track_label`` all live on the device, so
+    sub-clip i+1 can be enqueued before anything about sub-clip i is known on the host.  Inputs per sub-clip are the
+    LOCAL labels (cluster_label_start=1; clustering is label-offset invariant) with their per-frame counts and cluster
+    count still on the device -- exactly what ``SubclipPipeline.submit`` leaves there."""
+
+    def __init__(self, num_frames, frame_capacity, device, max_instances=20, max_labels=None, max_subclips=None):
+        from stemseg_b200 import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.num_frames, self.frame_capacity, self.max_instances = int(num_frames), int(frame_capacity), int(max_instances)
+        if max_labels is None:
+            max_labels = self.max_instances * (max_subclips if max_subclips is not None else max(1, self.num_frames))
+        self.max_labels = int(max_labels)
+        with torch.cuda.device(self.device):
+            self.frame_labels = torch.empty((self.num_frames, self.frame_capacity), dtype=torch.int64, device=self.device)
+            self.frame_count = torch.full((self.num_frames,), -1, dtype=torch.int32, device=self.device)
+            # one int32 block so that the end-of-video read-back is a single copy:
+            # [state 4][span_lo L+1][span_hi L+1][track_counts (L+1) x int64 as 2 x int32]
+            n = self.max_labels + 1
+            self._block = torch.empty(4 + 4 * n + 4, dtype=torch.int32, device=self.device)
+            self.state = self._block[0:4]
+            self.span_lo = self._block[4:4 + n]
+            self.span_hi = self._block[4 + n:4 + 2 * n]
+            off = 4 + 2 * n
+            off += off % 2                                   # 8-byte alignment of the int64 view
+            self.track_counts = self._block[off:off + 2 * n].view(torch.int64)
+            self._ws = {}
+        self.reset()
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            self.frame_count.fill_(-1)
+            self.state.zero_()
+            self.state[0:1].fill_(1)                         # next_track_label starts at 1 (online_chainer.py:162)
+            self.span_lo.fill_(10000)
+            self.span_hi.fill_(-1)
+            self.track_counts.zero_()
+        self._subclips = []
+        self._prev_frames = None
+
+    @torch.no_grad()
+    def add_subclip(self, frames, labels, frame_counts_dev, k_dev):
+        """frames: list of global frame numbers; labels: int64 CUDA tensor (capacity >= sum of counts) with the local
+        labels, rewritten in place; frame_counts_dev: int32 CUDA tensor [len(frames)]; k_dev: int32 CUDA tensor [1]
+        (number of clusters).  Returns the device tensor of this sub-clip's instance_labels (int64 [max_instances],
+        -1 padding), valid once the stream has run."""
+        lib, _lib = self.lib, self._lib
+        frames = [int(t) for t in frames]
+        nf = len(frames)
+        first = self._prev_frames is None
+        prev = set() if first else set(self._prev_frames)
+        overlap = [1 if t in prev else 0 for t in frames]
+        if not first and not any(overlap):
+            raise ValueError("sub-clip shares no frame with the previous one: nothing to associate it through")
+        if labels.dtype != torch.int64 or not labels.is_cuda or not labels.is_contiguous():
+            raise ValueError("labels must be a contiguous int64 CUDA tensor")
+        if frame_counts_dev.dtype != torch.int32 or frame_counts_dev.numel() < nf or k_dev.dtype != torch.int32:
+            raise ValueError("frame counts / cluster count must be int32 CUDA tensors")
+        arr = (_lib.c_int32 * nf)
+        with torch.cuda.device(self.device):
+            ws = self._ws.get(nf)
+            if ws is None:
+                nbytes = lib.stemseg_stitch_workspace_bytes(self.max_instances, nf, self.max_labels)
+                ws = self._ws[nf] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            meta = torch.empty(self.max_instances, dtype=torch.int64, device=self.device)
+            _lib.check(lib.stemseg_stitch_subclip(
+                _lib.ptr(labels), labels.numel(), _lib.ptr(frame_counts_dev), _lib.ptr(k_dev), arr(*frames), arr(*overlap),
+                nf, 1 if first else 0, self.max_instances, _lib.ptr(self.frame_labels), _lib.ptr(self.frame_count),
+                self.frame_capacity, self.num_frames, _lib.ptr(self.state), _lib.ptr(self.track_counts),
+                _lib.ptr(self.span_lo), _lib.ptr(self.span_hi), self.max_labels, _lib.ptr(meta), _lib.ptr(ws),
+                ws.numel(), _lib.stream_ptr()))
+        self._prev_frames = frames
+        self._subclips.append((frames, labels, frame_counts_dev, meta))
+        return meta
+
+    @torch.no_grad()
+    def finish(self, subseq_meta=None):
+        """The one synchronisation of the video: fetch state + statistics + per-frame counts, raise on device-side
+        errors, and return (DeviceTrackContainer, per-sub-clip relabelled label tensors, metas) like
+        ``stitch_subsequences_device``."""
+        with torch.cuda.device(self.device):
+            host = torch.cat([self._block, self.frame_count]).cpu()
+        n = self.max_labels + 1
+        state = host[0:4].tolist()
+        if state[2]:
+            msgs = [m for bit, m in STITCH_ERRORS.items() if state[2] & bit]
+            raise AssertionError("device stitch failed: " + "; ".join(msgs))
+        lo = host[4:4 + n].tolist()
+        hi = host[4 + n:4 + 2 * n].tolist()
+        off = 4 + 2 * n
+        off += off % 2
+        cnt = host[off:off + 2 * n].view(torch.int64).tolist()
+        fcount = host[self._block.numel():].tolist()
+        counts = defaultdict(lambda: 0)
+        spans = defaultdict(lambda: [10000, -1])
+        for idx in range(n):
+            if cnt[idx] > 0:
+                counts[idx - 1] = cnt[idx]
+                spans[idx - 1] = [lo[idx], hi[idx]]
+        frame_labels = [self.frame_labels[t, :fcount[t]] if fcount[t] >= 0 else None for t in range(self.num_frames)]
+        out_labels, out_meta = [], []
+        metas_host = torch.stack([m for _, _, _, m in self._subclips]).cpu().tolist() if self._subclips else []
+        for i, (frames, labels, _, _) in enumerate(self._subclips):
+            total = sum(fcount[t] for t in frames)
+            out_labels.append(labels[:total])
+            meta = None
+            if subseq_meta is not None:
+                meta = dict(subseq_meta[i])
+                k = len(meta['instance_labels'])
+                meta['instance_labels'] = [int(v) for v in metas_host[i][:k]]
+            else:
+                meta = {'instance_labels': [int(v) for v in metas_host[i] if v >= 0]}
+            out_meta.append(meta)
+        self.next_track_label = state[0]
+        return DeviceTrackContainer(frame_labels, counts, spans), out_labels, out_meta

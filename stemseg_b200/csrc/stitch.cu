@@ -97,3 +97,296 @@ extern "C" int32_t stemseg_relabel_lut(int64_t* labels, int64_t n, int64_t base,
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident sequential stitch (OnlineChainer.process, online_chainer.py:162-236, for one sub-clip per call):
+//   stitch_hist    one pass over the sub-clip's points: per-frame label counts + the joint histogram
+//                  (existing track label x current local label) over the overlap frames
+//   stitch_assign  one thread: label lists in CPython set order, IoU costs in the reference's fp32/fp64 arithmetic,
+//                  scipy's assignment algorithm (assoc.cuh), relabelling tables, TrackContainer statistics
+//                  (get_track_mask_idxes, online_chainer.py:94-117), next_track_label -- all kept on the device
+//   stitch_relabel one pass: local labels -> track ids, non-overlap frames stored into the container
+// Nothing is read back per sub-clip; the caller fetches the error word / statistics once at the end of the video.
+// ---------------------------------------------------------------------------------------------------------------
+#include "assoc.cuh"
+
+namespace stemseg {
+namespace {
+
+constexpr int kStitchMaxFrames = 64;
+constexpr int kStitchThreads = 256;
+
+enum StitchError {
+    kErrLabelRange = 1, kErrOverlapSize = 2, kErrLabelsOverlap = 4, kErrTooManyLabels = 8, kErrFrameExists = 16,
+    kErrAssignment = 32
+};
+
+struct StitchFrames {
+    int n_frames;
+    int frame[kStitchMaxFrames];         // global frame number of every slot
+    int overlap[kStitchMaxFrames];       // 1: the frame is already in the container (shared with the previous sub-clip)
+};
+
+struct StitchArgs {
+    long long* labels;                   // [>= total points] local labels (start 1), rewritten to the returned labels
+    const int* frame_counts;             // device [n_frames]
+    const int* k_dev;                    // device: clusters of this sub-clip
+    int max_instances;
+    long long* frame_labels;             // container [num_frames][frame_capacity]
+    int* frame_count;                    // container [num_frames], -1 = no labels yet
+    long long frame_capacity;
+    int* state;                          // [0] next_track_label [1] highest [2] error flags [3] sub-clips done
+    long long* track_counts;             // [max_labels + 1], index = label + 1
+    int* span_lo;                        // [max_labels + 1]
+    int* span_hi;
+    int max_labels;
+    long long* meta_labels;              // [max_instances] out: track id of every local cluster ordinal
+    // workspace
+    int* joint;                          // [(max_labels + 1)][max_instances + 2]
+    int* per_frame;                      // [max_instances + 2][n_frames]
+    long long* lut_assoc;                // [max_instances + 1]
+    long long* lut_local;                // [max_instances + 1]
+    double* cost;                        // [kAssocMaxSide * kAssocMaxSide]
+    LsapScratch* lsap;
+    int is_first;
+};
+
+__device__ __forceinline__ int find_slot(const long long* starts, int n_frames, long long p) {
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {                    // last slot with starts[slot] <= p
+        const int mid = (lo + hi + 1) >> 1;
+        if (starts[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kStitchThreads) stitch_hist_kernel(const StitchArgs a, const StitchFrames f) {
+    __shared__ long long starts[kStitchMaxFrames + 1];
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int j = 0; j < f.n_frames; ++j) { starts[j] = s; s += a.frame_counts[j]; }
+        starts[f.n_frames] = s;
+    }
+    __syncthreads();
+    const long long total = starts[f.n_frames];
+    const int k = *a.k_dev;
+    const int nb = a.max_instances + 2;
+    int err = 0;
+    for (long long p = blockIdx.x * 1ll * kStitchThreads + threadIdx.x; p < total; p += 1ll * gridDim.x * kStitchThreads) {
+        const int j = find_slot(starts, f.n_frames, p);
+        const long long l = a.labels[p];
+        if (l == 0 || l > k || l < -1) { err |= kErrLabelRange; continue; }
+        const int lbin = l < 0 ? 0 : static_cast<int>(l);
+        atomicAdd(&a.per_frame[lbin * f.n_frames + j], 1);
+        if (!a.is_first && f.overlap[j]) {
+            const int t = f.frame[j];
+            if (a.frame_count[t] != a.frame_counts[j]) { err |= kErrOverlapSize; continue; }
+            const long long e = a.frame_labels[t * a.frame_capacity + (p - starts[j])];
+            if (e == 0 || e > a.max_labels || e < -1) { err |= kErrLabelRange; continue; }
+            const int gbin = e < 0 ? 0 : static_cast<int>(e);
+            atomicAdd(&a.joint[gbin * nb + lbin], 1);
+        }
+    }
+    if (err) atomicOr(&a.state[2], err);
+}
+
+__global__ void stitch_assign_kernel(const StitchArgs a, const StitchFrames f) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int k = *a.k_dev;
+    const int nb = a.max_instances + 2;
+    const long long offset = a.state[0] - 1;
+    int err = 0;
+    if (k > a.max_instances || offset + k > a.max_labels) err |= kErrTooManyLabels;
+    for (int l = 1; l <= a.max_instances + 1; ++l) {
+        a.lut_local[l - 1] = offset + l;
+        a.lut_assoc[l - 1] = offset + l;
+    }
+    for (int c = 0; c < a.max_instances; ++c) a.meta_labels[c] = c < k ? offset + c + 1 : -1;
+    for (int j = 0; j < f.n_frames; ++j) {
+        const int t = f.frame[j];
+        if (!a.is_first && f.overlap[j]) {
+            if (a.frame_count[t] != a.frame_counts[j]) err |= kErrOverlapSize;
+        } else if (a.frame_count[t] >= 0) {
+            err |= kErrFrameExists;
+        }
+    }
+    if (!a.is_first && !(err & kErrTooManyLabels)) {
+        long long vals1[kAssocMaxSide + 1], vals2[kAssocMaxSide + 1], u1[kAssocMaxSide + 1], u2[kAssocMaxSide + 1];
+        long long size_b[kAssocMaxSide + 2];
+        int n1 = 0, n2 = 0;
+        const int highest = a.state[1];
+        // existing labels present in the overlap frames (ascending, like Tensor.unique()), outliers first
+        for (int g = 0; g <= highest && g <= a.max_labels; ++g) {
+            long long s = 0;
+            for (int l = 0; l <= k; ++l) s += a.joint[g * nb + l];
+            if (s > 0) {
+                if (n1 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
+                vals1[n1++] = g == 0 ? -1 : g;
+            }
+        }
+        for (int l = 0; l <= k && l < kAssocMaxSide + 2; ++l) {
+            long long s = 0;
+            for (int g = 0; g <= highest && g <= a.max_labels; ++g) s += a.joint[g * nb + l];
+            size_b[l] = s;
+            if (s > 0) {
+                if (n2 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
+                vals2[n2++] = l == 0 ? -1 : offset + l;
+            }
+        }
+        if (!err) {
+            const int c1 = pyset_order(vals1, n1, u1);
+            const int c2 = pyset_order(vals2, n2, u2);
+            if (c1 < 0 || c2 < 0) err |= kErrTooManyLabels;
+            else {
+                // every current label is > every existing one (offset = next_track_label - 1 >= highest existing label)
+                for (int i = 0; i < c1; ++i)
+                    if (u1[i] > offset) err |= kErrLabelsOverlap;
+                for (int i1 = 0; i1 < c1; ++i1) {
+                    long long size1 = 0;
+                    for (int l = 0; l <= k; ++l) size1 += a.joint[u1[i1] * nb + l];
+                    for (int i2 = 0; i2 < c2; ++i2) {
+                        const int l = static_cast<int>(u2[i2] - offset);
+                        const long long inter = a.joint[u1[i1] * nb + l];
+                        const long long uni = size1 + size_b[l] - inter;
+                        const float iou = __fdiv_rn(static_cast<float>(inter), static_cast<float>(uni));   // fp32 tensors
+                        const float c32 = static_cast<float>(1.0 - static_cast<double>(iou));            // 1. - iou.item()
+                        a.cost[i1 * c2 + i2] = static_cast<double>(c32);
+                    }
+                }
+                int rows[kAssocMaxSide], cols[kAssocMaxSide];
+                const int pairs = lsap_solve(a.cost, c1, c2, rows, cols, *a.lsap);
+                if (pairs < 0) err |= kErrAssignment;
+                for (int q = 0; q < pairs; ++q) {
+                    const long long associated = u1[rows[q]], current = u2[cols[q]];
+                    a.lut_assoc[current - offset - 1] = associated;
+                    for (int c = 0; c < k; ++c)                   // meta_info['instance_labels'].index(current)
+                        if (a.meta_labels[c] == current) { a.meta_labels[c] = associated; break; }
+                }
+            }
+        }
+    }
+    // TrackContainer bookkeeping for the frames added by this sub-clip
+    int highest = a.state[1];
+    for (int j = 0; j < f.n_frames; ++j) {
+        if (!a.is_first && f.overlap[j]) continue;
+        const int t = f.frame[j];
+        a.frame_count[t] = a.frame_counts[j];
+        for (int lbin = 0; lbin <= k && lbin <= a.max_instances; ++lbin) {
+            const int c = a.per_frame[lbin * f.n_frames + j];
+            if (c == 0) continue;
+            const long long label = lbin == 0 ? -1 : a.lut_assoc[lbin - 1];
+            if (label > a.max_labels) { err |= kErrTooManyLabels; continue; }
+            a.track_counts[label + 1] += c;
+            if (t < a.span_lo[label + 1]) a.span_lo[label + 1] = t;
+            if (t > a.span_hi[label + 1]) a.span_hi[label + 1] = t;
+            if (label > highest) highest = static_cast<int>(label);
+        }
+    }
+    a.state[1] = highest;
+    a.state[0] = highest + 1;
+    a.state[3] += 1;
+    if (err) atomicOr(&a.state[2], err);
+}
+
+__global__ void __launch_bounds__(kStitchThreads) stitch_relabel_kernel(const StitchArgs a, const StitchFrames f) {
+    __shared__ long long starts[kStitchMaxFrames + 1];
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int j = 0; j < f.n_frames; ++j) { starts[j] = s; s += a.frame_counts[j]; }
+        starts[f.n_frames] = s;
+    }
+    __syncthreads();
+    const long long total = starts[f.n_frames];
+    for (long long p = blockIdx.x * 1ll * kStitchThreads + threadIdx.x; p < total; p += 1ll * gridDim.x * kStitchThreads) {
+        const int j = find_slot(starts, f.n_frames, p);
+        const long long l = a.labels[p];
+        const bool over = !a.is_first && f.overlap[j];
+        long long out = -1;
+        if (l >= 1 && l <= a.max_instances + 1) out = over ? a.lut_local[l - 1] : a.lut_assoc[l - 1];
+        a.labels[p] = out;
+        if (!over) a.frame_labels[f.frame[j] * a.frame_capacity + (p - starts[j])] = out;
+    }
+}
+
+size_t stitch_ws_layout(int max_instances, int n_frames, int max_labels, size_t* off) {
+    size_t o = 0;
+    off[0] = o; o = align_up(o + sizeof(int) * (static_cast<size_t>(max_labels) + 1) * (max_instances + 2), 256);   // joint
+    off[1] = o; o = align_up(o + sizeof(int) * static_cast<size_t>(max_instances + 2) * n_frames, 256);              // per_frame
+    off[2] = o; o = align_up(o + sizeof(long long) * (max_instances + 1), 256);                                       // lut_assoc
+    off[3] = o; o = align_up(o + sizeof(long long) * (max_instances + 1), 256);                                       // lut_local
+    off[4] = o; o = align_up(o + sizeof(double) * kAssocMaxSide * kAssocMaxSide, 256);                                // cost
+    off[5] = o; o = align_up(o + sizeof(LsapScratch), 256);
+    return o;
+}
+
+}  // namespace
+}  // namespace stemseg
+
+extern "C" size_t stemseg_stitch_workspace_bytes(int32_t max_instances, int32_t n_frames, int32_t max_labels) {
+    size_t off[6];
+    return stitch_ws_layout(max_instances, n_frames, max_labels, off);
+}
+
+extern "C" int32_t stemseg_stitch_subclip(int64_t* labels, int64_t capacity, const int32_t* frame_counts_dev,
+                                          const int32_t* k_dev, const int32_t* frames_host, const int32_t* overlap_host,
+                                          int32_t n_frames, int32_t is_first, int32_t max_instances,
+                                          int64_t* frame_labels, int32_t* frame_count, int64_t frame_capacity,
+                                          int32_t num_frames, int32_t* state, int64_t* track_counts, int32_t* span_lo,
+                                          int32_t* span_hi, int32_t max_labels, int64_t* meta_labels_out,
+                                          void* workspace, size_t ws_bytes, void* stream_) {
+    SS_REQUIRE(labels && frame_counts_dev && k_dev && frames_host && overlap_host && frame_labels && frame_count && state &&
+                   track_counts && span_lo && span_hi && meta_labels_out && workspace,
+               "stitch_subclip: null pointer");
+    SS_REQUIRE(n_frames >= 1 && n_frames <= kStitchMaxFrames, "stitch_subclip: n_frames %d out of range [1, %d]", n_frames,
+               kStitchMaxFrames);
+    SS_REQUIRE(max_instances >= 1 && max_instances + 2 <= kAssocMaxSide, "stitch_subclip: max_instances %d out of range",
+               max_instances);
+    SS_REQUIRE(max_labels >= max_instances && capacity >= 0 && frame_capacity >= 1 && num_frames >= 1,
+               "stitch_subclip: bad sizes");
+    size_t off[6];
+    const size_t need = stitch_ws_layout(max_instances, n_frames, max_labels, off);
+    SS_REQUIRE(ws_bytes >= need, "stitch_subclip: workspace too small (%zu < %zu)", ws_bytes, need);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    StitchFrames f;
+    f.n_frames = n_frames;
+    for (int j = 0; j < n_frames; ++j) {
+        SS_REQUIRE(frames_host[j] >= 0 && frames_host[j] < num_frames, "stitch_subclip: frame %d outside the video",
+                   frames_host[j]);
+        f.frame[j] = frames_host[j];
+        f.overlap[j] = overlap_host[j] ? 1 : 0;
+    }
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    StitchArgs a;
+    a.labels = reinterpret_cast<long long*>(labels);
+    a.frame_counts = frame_counts_dev;
+    a.k_dev = k_dev;
+    a.max_instances = max_instances;
+    a.frame_labels = reinterpret_cast<long long*>(frame_labels);
+    a.frame_count = frame_count;
+    a.frame_capacity = frame_capacity;
+    a.state = state;
+    a.track_counts = reinterpret_cast<long long*>(track_counts);
+    a.span_lo = span_lo;
+    a.span_hi = span_hi;
+    a.max_labels = max_labels;
+    a.meta_labels = reinterpret_cast<long long*>(meta_labels_out);
+    a.joint = reinterpret_cast<int*>(ws + off[0]);
+    a.per_frame = reinterpret_cast<int*>(ws + off[1]);
+    a.lut_assoc = reinterpret_cast<long long*>(ws + off[2]);
+    a.lut_local = reinterpret_cast<long long*>(ws + off[3]);
+    a.cost = reinterpret_cast<double*>(ws + off[4]);
+    a.lsap = reinterpret_cast<LsapScratch*>(ws + off[5]);
+    a.is_first = is_first ? 1 : 0;
+    SS_CUDA_OK(cudaMemsetAsync(ws + off[0], 0, off[2] - off[0], stream));          // joint + per_frame
+    long long blocks = (capacity + kStitchThreads * 4 - 1) / (kStitchThreads * 4);
+    const long long cap = 2ll * device_sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    stitch_hist_kernel<<<static_cast<unsigned>(blocks), kStitchThreads, 0, stream>>>(a, f);
+    SS_CUDA_OK(cudaGetLastError());
+    stitch_assign_kernel<<<1, 32, 0, stream>>>(a, f);
+    SS_CUDA_OK(cudaGetLastError());
+    stitch_relabel_kernel<<<static_cast<unsigned>(blocks), kStitchThreads, 0, stream>>>(a, f);
+    SS_CUDA_OK(cudaGetLastError());
+    return STEMSEG_OK;
+}

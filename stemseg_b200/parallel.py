@@ -125,39 +125,99 @@ def exchange_and_stitch_device(num_frames, subseq_frames, local_results, group=N
     return stitch_subsequences_device(num_frames, subseq_frames, labels, counts, ks, metas)
 
 
+def _meta_dict(words, e, max_instances, offset_labels):
+    """Clustering meta words (host int32 tensor) -> the reference's meta dict (clusterers.py:161-166) with the given
+    (already stitched) instance labels."""
+    k = int(words[0])
+    floats = words[4 + max_instances:].view(torch.float32)
+    centers = floats[:max_instances * e].reshape(max_instances, e)[:k]
+    bws = floats[max_instances * e:2 * max_instances * e].reshape(max_instances, e)[:k]
+    return {"instance_labels": list(offset_labels), "instance_centers": [c.tolist() for c in centers],
+            "instance_stds": [(1. / b).clamp(min=1e-8).sqrt().tolist() for b in bws], "instance_masks": []}
+
+
 @torch.no_grad()
 def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, group=None):
     """Run the owned sub-clips through ``pipeline`` (stemseg_b200.pipeline.SubclipPipeline) and stitch globally.
 
     masks: [T,h,w] foreground masks of the whole video (None is only accepted for a single sub-clip: per-sub-clip
     seediness thresholds would give overlap frames different point sets in different sub-clips);
-    features_for_clip(i) -> {scale: tensor} pyramid of sub-clip i (only called for owned sub-clips)."""
+    features_for_clip(i) -> {scale: tensor} pyramid of sub-clip i (only called for owned sub-clips).
+
+    Nothing is synchronised with the host until the whole video is stitched: every owned sub-clip is enqueued
+    (``submit``), its local labels / per-frame counts / clustering meta words are copied device-to-device into two
+    fixed-layout exchange buffers, ONE all_gather per buffer (NCCL) makes every sub-clip visible on every rank, and the
+    sequential stitch runs on the device (``DeviceStitcher``: histogram -> assignment -> relabel kernels per sub-clip).
+    The only device->host copy is the final one in ``DeviceStitcher.finish``."""
+    from stemseg_b200.chaining import DeviceStitcher
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if masks is None and len(subseq_frames) > 1:
+    n_sub = len(subseq_frames)
+    if masks is None and n_sub > 1:
         # a per-sub-clip seediness threshold gives overlap frames a different point set in each sub-clip; the stitch
         # needs identical points there (the reference averages seediness / semseg per frame over all sub-clips first,
         # inference/main.py:93-103) -> build the video masks with FrameAverager.foreground_index and pass them in
         raise ValueError("clip_parallel_process needs the video's foreground masks when there is more than one "
                          "sub-clip (build them with stemseg_b200.foreground.FrameAverager)")
+    if not (hasattr(pipeline, "submit") and getattr(pipeline, "use_step_graph", False)) or masks is None:
+        return _clip_parallel_process_eager(pipeline, masks, subseq_frames, features_for_clip, group)
+    dev = pipeline.clusterer.device
+    num_frames = max(max(f) for f in subseq_frames) + 1
+    max_t = max(len(f) for f in subseq_frames)
+    cap = int(masks.shape[-2]) * int(masks.shape[-1])
+    max_local = (n_sub + world - 1) // world
+    mi = pipeline.clusterer.max_instances
+    e_dims = pipeline.embedding_head.embedding_size
+    from stemseg_b200 import _lib
+    meta_words = int(_lib.load().stemseg_seq_cluster_meta_words(e_dims, mi))
+    hdr = max_t + 1 + meta_words
+    with torch.cuda.device(dev):
+        labels_buf = torch.empty((max_local, max_t * cap), dtype=torch.int64, device=dev)
+        head_buf = torch.zeros((max_local, hdr), dtype=torch.int32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        for slot, i in enumerate(shard_subclips(n_sub, rank, world)):
+            frames = subseq_frames[i]
+            pend = pipeline.submit(features_for_clip(i), fg_mask=masks[frames], cluster_label_start=1)
+            view = pend.device_view()
+            main.wait_event(view["done"])
+            for key in ("labels", "counts", "meta"):        # allocated on the pipeline's stream, consumed on this one
+                view[key].record_stream(main)
+            t_i = len(frames)
+            labels_buf[slot, :view["labels"].numel()].copy_(view["labels"], non_blocking=True)
+            head_buf[slot, :t_i].copy_(view["counts"][:t_i], non_blocking=True)
+            head_buf[slot, max_t:max_t + 1 + meta_words].copy_(
+                torch.cat([view["meta"][0:1], view["meta"]]), non_blocking=True)         # [K][meta words]
+        if world > 1:
+            all_labels = torch.empty((world,) + tuple(labels_buf.shape), dtype=torch.int64, device=dev)
+            all_head = torch.empty((world,) + tuple(head_buf.shape), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(all_labels, labels_buf, group=group)
+            dist.all_gather_into_tensor(all_head, head_buf, group=group)
+        else:
+            all_labels, all_head = labels_buf.unsqueeze(0), head_buf.unsqueeze(0)
+        stitcher = DeviceStitcher(num_frames, cap, dev, max_instances=mi, max_subclips=n_sub)
+        for i, frames in enumerate(subseq_frames):
+            r, slot = i % world, i // world
+            stitcher.add_subclip(frames, all_labels[r, slot], all_head[r, slot, :len(frames)],
+                                 all_head[r, slot, max_t:max_t + 1])
+        head_host = all_head.cpu()                      # stream-ordered after the stitch kernels: the video's one sync
+        container, out_labels, out_meta = stitcher.finish()
+    metas = []
+    for i in range(n_sub):
+        r, slot = i % world, i // world
+        metas.append(_meta_dict(head_host[r, slot, max_t + 1:], e_dims, mi, out_meta[i]["instance_labels"]))
+    return container, out_labels, metas
+
+
+@torch.no_grad()
+def _clip_parallel_process_eager(pipeline, masks, subseq_frames, features_for_clip, group=None):
+    """Fallback for pipelines without the graphed submit() path: per-sub-clip results on the host, then
+    ``exchange_and_stitch_device``."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
     local = {}
-
-    def collect(i, pend):
-        res = pend.result()
-        local[i] = (res.labels, list(res.fg_index.frame_counts), res.meta)
-
-    queue = []
-    depth = max(1, getattr(pipeline, "steps_in_flight", 1))
     for i in shard_subclips(len(subseq_frames), rank, world):
         fg_mask = None if masks is None else masks[subseq_frames[i]]
-        if hasattr(pipeline, "submit") and getattr(pipeline, "use_step_graph", False):
-            queue.append((i, pipeline.submit(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)))
-            if len(queue) > depth:
-                collect(*queue.pop(0))
-        else:
-            res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
-            local[i] = (res.labels, list(res.fg_index.frame_counts), res.meta)
-    for item in queue:
-        collect(*item)
+        res = pipeline(features_for_clip(i), fg_mask=fg_mask, cluster_label_start=1)
+        local[i] = (res.labels, list(res.fg_index.frame_counts), res.meta)
     num_frames = max(max(f) for f in subseq_frames) + 1
     return exchange_and_stitch_device(num_frames, subseq_frames, local, group=group)

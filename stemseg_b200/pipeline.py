@@ -28,6 +28,14 @@ class PendingStep(object):
         self._result = None
         self.inputs_consumed = None      # CUDA event: the step no longer reads the caller's feature tensors
 
+    def device_view(self):
+        """What a device-resident consumer needs, WITHOUT synchronising: local labels (capacity-sized int64, valid
+        entries = the first counts[-1]), per-frame counts (int32 [T+1], last = total), clustering meta words (int32,
+        word 0 = number of clusters; see stemseg_seq_cluster_meta_words) and the CUDA event that marks them complete."""
+        return {"labels": self._snap["labels"], "counts": self._snap["counts"], "meta": self._snap["meta"],
+                "done": self._done, "max_instances": self._pipe.clusterer.max_instances,
+                "embedding_dims": self._state["pending"]["e"]}
+
     def result(self):
         if self._result is not None:
             return self._result
@@ -233,7 +241,8 @@ class SubclipPipeline(object):
             # stream-ordered snapshots: the next replay may overwrite the graph's static buffers right after these
             snap = {"labels": st["pending"]["labels"].clone(), "primary": st["pending"]["primary"].clone(),
                     "indices": st["fg"].capacity_indices.clone(), "emb": st["emb"].clone(), "var": st["var"].clone(),
-                    "seed": st["seed"].clone(), "semseg": None if st["semseg"] is None else st["semseg"].clone()}
+                    "seed": st["seed"].clone(), "semseg": None if st["semseg"] is None else st["semseg"].clone(),
+                    "counts": st["fg"].counts_dev.clone(), "meta": st["pending"]["meta"].clone()}
             counts_host = torch.empty(st["fg"].counts_dev.shape, dtype=torch.int32, pin_memory=True)
             meta_host = torch.empty(st["pending"]["meta"].shape, dtype=torch.int32, pin_memory=True)
             counts_host.copy_(st["fg"].counts_dev, non_blocking=True)
