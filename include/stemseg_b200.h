@@ -444,6 +444,11 @@ int32_t stemseg_scale_by_device_scalar(float* x, int64_t n, const float* scalar,
  * ---------------------------------------------------------------------------------------------------------- */
 int32_t stemseg_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                          float weight_decay, float grad_scale, int32_t nesterov, void* stream);
+/* Same step with {lr, momentum, weight_decay, grad_scale} read from DEVICE memory (float[4]) at run time: a CUDA graph
+ * that captured this launch follows the learning-rate schedule (training/main.py:209-210 steps the scheduler every
+ * iteration) by updating the array, without re-capture. */
+int32_t stemseg_sgd_step_dev(float* param, const float* grad, float* momentum_buf, int64_t n, const float* hyper,
+                             int32_t nesterov, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -123,6 +123,7 @@ PROTOTYPES = {
     "stemseg_scale_by_device_scalar": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "stemseg_sgd_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32,
                                    c_void_p]),
+    "stemseg_sgd_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]),
     "stemseg_conv3d_auto_split": (c_int32, [ctypes.POINTER(StemsegConvShape)]),
     "stemseg_group_norm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
     "stemseg_group_norm_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_float,
@@ -160,7 +161,7 @@ KERNELS_PER_CALL = {
     "stemseg_pool_relu_backward": 1, "stemseg_group_norm_backward": 3, "stemseg_channel_sum": 2,
     "stemseg_to_planes": 1, "stemseg_transpose_pad": 1, "stemseg_conv3d_wgrad": 1, "stemseg_wgrad_reduce": 1,
     "stemseg_conv3d_wgrad_direct": 1,
-    "stemseg_scale_by_device_scalar": 1, "stemseg_sgd_step": 1,
+    "stemseg_scale_by_device_scalar": 1, "stemseg_sgd_step": 1, "stemseg_sgd_step_dev": 1,
     "stemseg_group_norm_backward_planes": 4, "stemseg_semseg_loss": 2, "stemseg_upsample_add_f32": 1, "stemseg_head_output_x": 1, "stemseg_head_backward_x": 2,
     # stemseg_embedding_loss launches a shape-dependent number of kernels: counted by losses.py
 }
@@ -243,3 +244,31 @@ class capture_guard(object):
         if self._was_enabled:
             gc.enable()
         return False
+
+
+class LRUCache(object):
+    """Bounded cache of captured CUDA graphs: every entry owns a private memory pool (saved activations, gradient
+    buffers), so an unbounded dict keyed on input shapes grows until the GPU is full."""
+
+    def __init__(self, capacity):
+        from collections import OrderedDict
+        self.capacity = max(1, int(capacity))
+        self._d = OrderedDict()
+
+    def get(self, key):
+        if key in self._d:
+            self._d.move_to_end(key)
+            return self._d[key]
+        return None
+
+    def put(self, key, value):
+        self._d[key] = value
+        self._d.move_to_end(key)
+        while len(self._d) > self.capacity:
+            self._d.popitem(last=False)              # dropping the entry releases its graphs and their pool
+
+    def __len__(self):
+        return len(self._d)
+
+    def __contains__(self, key):
+        return key in self._d

@@ -185,11 +185,22 @@ def _dst(grad_dst, name, params):
     return torch.empty_like(params[name])
 
 
-def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=True):
+EARLY_BLOCKS = (0, 1)        # block_32x, block_16x: 81 % of a head's parameters, a few % of its backward time
+LATE_BLOCKS = (2, 3)         # block_8x, block_4x: the long dgrad / wgrad launches
+
+
+def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=True, phase="all", carry=None):
     """-> (list of 4 feature gradients [1,C,T,h,w] (None when not needed), {parameter name: gradient}).
 
     grad_dst: optional {parameter name: tensor of the parameter's shape}; gradients are WRITTEN there (e.g. views
-    into a flat all-reduce buffer) instead of into fresh tensors."""
+    into a flat all-reduce buffer) instead of into fresh tensors.
+
+    phase: "all", or the two halves used by the data-parallel trainer to overlap the gradient exchange with the long
+    part of the backward pass: "early" = output heads, merges and the low-resolution blocks (block_32x / block_16x,
+    whose gradients are most of the bytes) -> returns (carry, grads so far); "late" (with that carry) = block_8x /
+    block_4x -> returns (feature gradients, remaining grads)."""
+    if phase == "late":
+        return _backward_blocks(head, saved, carry, grad_dst, need_feature_grads, LATE_BLOCKS, final=True)
     lib = _lib.load()
     planes, tscale = saved["planes"], saved["tscale"]
     spec = saved["out_spec"]
@@ -233,10 +244,24 @@ def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=T
         grads[merge + ".weight"] = wgrad_dst
         d_high = d_xin
     branch_grad[0] = d_high
+    carry = {"branch_grad": branch_grad, "grads": grads, "feat_grads": [None] * 4, "params": params,
+             "dgrad_w": dgrad_w}
+    if phase == "early":
+        _backward_blocks(head, saved, carry, grad_dst, need_feature_grads, EARLY_BLOCKS, final=False)
+        return carry, carry["grads"]
+    return _backward_blocks(head, saved, carry, grad_dst, need_feature_grads, EARLY_BLOCKS + LATE_BLOCKS, final=True)
 
-    # ---- conv stages, last stage first -----------------------------------------------------------------------------
-    feat_grads = []
+
+def _backward_blocks(head, saved, carry, grad_dst, need_feature_grads, which, final):
+    """Backward of the conv stages of the scale blocks `which` (indices into D.BLOCKS), last stage first."""
+    lib = _lib.load()
+    planes = saved["planes"]
+    branch_grad, grads, feat_grads = carry["branch_grad"], carry["grads"], carry["feat_grads"]
+    params, dgrad_w = carry["params"], carry["dgrad_w"]
+    dev = branch_grad[0].device
     for b, (name, n_stages) in enumerate(D.BLOCKS):
+        if b not in which:
+            continue
         d = branch_grad[b]
         for j in reversed(range(n_stages)):
             st = saved["blocks"][name][j]
@@ -286,7 +311,7 @@ def training_backward(head, saved, grad_out, grad_dst=None, need_feature_grads=T
                 d = None
             else:
                 d = D.conv3d(dy_p, dgrad_w[wname])                   # dgrad: conv with flipped / transposed weights
-        feat_grads.append(None if d is None else d.permute(0, 4, 1, 2, 3))      # NDHWC -> NCTHW view
+        feat_grads[b] = None if d is None else d.permute(0, 4, 1, 2, 3)          # NDHWC -> NCTHW view
     if grad_dst is not None:                                         # small gradients: copy into their slots
         for name, gr in grads.items():
             if gr.data_ptr() != grad_dst[name].data_ptr():

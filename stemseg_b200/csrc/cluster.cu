@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace stemseg {
@@ -39,6 +40,7 @@ struct ClusterArgs {
     unsigned int* meta;
     unsigned long long* best;    // [max_inst + 1] winner key per iteration (zeroed before launch)
     unsigned int* barrier;       // grid barrier counter (zeroed before launch)
+    unsigned int* avail;         // streaming variant: 1 bit per point, set while the point is unassigned
 };
 
 // Sum of E terms in the order ATen's CPU sum kernel uses for a contiguous inner reduction (SumKernel.cpp:
@@ -126,6 +128,7 @@ __device__ __forceinline__ unsigned long long make_key(float s, unsigned int idx
     return (static_cast<unsigned long long>(o) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
 }
 
+template <int THREADS = kThreads>
 __device__ __forceinline__ void publish_key(unsigned long long key, unsigned long long* slot,
                                             unsigned long long* s_red) {
     key = warp_max_u64(key);
@@ -133,7 +136,7 @@ __device__ __forceinline__ void publish_key(unsigned long long key, unsigned lon
     if (lane == 0) s_red[warp] = key;
     __syncthreads();
     if (warp == 0) {
-        key = lane < (kThreads / 32) ? s_red[lane] : 0ull;
+        key = lane < (THREADS / 32) ? s_red[lane] : 0ull;
         key = warp_max_u64(key);
         if (lane == 0 && key != 0ull) atomicMax(slot, key);
     }
@@ -317,6 +320,195 @@ __global__ void __launch_bounds__(kThreads) seq_cluster_kernel(const ClusterArgs
     }
 }
 
+
+// Streaming variant for point sets that do not fit the register-resident one (full-resolution clustering; HBM-bound).
+// State is split in two: `primary` (int32 ordinal of the claiming cluster, written once per point, read by the final
+// pass) and a 1-bit-per-point availability mask (N/8 bytes: L2-resident) that the iterations read instead -- an
+// assigned point costs 1/8 byte per iteration and a fully assigned 32-point group is skipped without touching its
+// embeddings.  Warp w owns the 32*UNROLL-point chunks w, w + W, ... (static mapping: only the owning warp ever reads or
+// writes a mask word); per trip it loads UNROLL mask words, then issues all embedding / seediness loads of the
+// available points (UNROLL x (E/4 + 1) independent 16-byte loads per lane) before the first distance is evaluated.
+template <int E, bool VEC, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS) seq_cluster_stream_kernel(const ClusterArgs a) {
+    long long n = a.n;
+    if (a.n_dev != nullptr) {
+        const long long nd = *a.n_dev;
+        if (nd < n) n = nd;
+    }
+    __shared__ float s_center[kMaxI][E];
+    __shared__ float s_bw[kMaxI][E];
+    __shared__ unsigned long long s_red[THREADS / 32];
+
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x) >> 5;
+    const long long total_warps = static_cast<long long>(gridDim.x) * (THREADS / 32);
+    const long long n_groups = (n + 31) / 32;
+    const long long n_chunks = (n_groups + UNROLL - 1) / UNROLL;
+    const long long tid0 = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+
+    {   // pass 0: everything unassigned (clusterers.py:96); winner of iteration 0
+        unsigned long long key = 0ull;
+        for (long long chunk = warp_global; chunk < n_chunks; chunk += total_warps) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long g = chunk * UNROLL + u;
+                const long long idx = g * 32 + lane;
+                const bool valid = idx < n;
+                if (valid) {
+                    a.primary[idx] = -1;
+                    const unsigned long long k = make_key(__ldg(a.seed + idx), static_cast<unsigned int>(idx));
+                    key = k > key ? k : key;
+                }
+                const unsigned int word = __ballot_sync(0xffffffffu, valid);
+                if (lane == 0 && g < n_groups) a.avail[g] = word;
+            }
+        }
+        publish_key<THREADS>(key, a.best + 0, s_red);
+    }
+    unsigned int generation = 1;
+    grid_barrier(a.barrier, generation);
+
+    int num_clusters = 0;
+    int exit_reason = 0;
+    for (int i = 0; i < a.max_inst; ++i) {                                  // clusterers.py:106
+        const unsigned long long w = __ldcg(a.best + i);
+        if (w == 0ull) { exit_reason = 1; break; }                          // clusterers.py:109-110
+        const unsigned int widx = 0xFFFFFFFFu - static_cast<unsigned int>(w & 0xFFFFFFFFull);
+        const float prob = __ldg(a.seed + widx);
+        if (prob < a.min_seed) { exit_reason = 2; break; }                  // clusterers.py:116-117
+        if (threadIdx.x < E) {                                              // clusterers.py:119,175
+            const int k = threadIdx.x;
+            s_center[i][k] = __ldg(a.emb + static_cast<long long>(widx) * E + k);
+            s_bw[i][k] = k < a.v ? __ldg(a.bw + static_cast<long long>(widx) * a.v + k) : a.free_bw[k - a.v];
+        }
+        __syncthreads();
+        num_clusters = i + 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.meta[4 + i] = widx;
+
+        float c[E], b[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { c[k] = s_center[i][k]; b[k] = s_bw[i][k]; }
+
+        unsigned long long key = 0ull;
+        for (long long chunk = warp_global; chunk < n_chunks; chunk += total_warps) {
+            unsigned int m[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long g = chunk * UNROLL + u;
+                m[u] = g < n_groups ? __ldcg(a.avail + g) : 0u;              // clusterers.py:107
+            }
+            float x[UNROLL][E];
+            float sd[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if ((m[u] >> lane) & 1u) {
+                    const long long idx = (chunk * UNROLL + u) * 32 + lane;
+                    load_point<E, VEC>(a.emb, idx, x[u]);
+                    sd[u] = __ldg(a.seed + idx);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (m[u] == 0u) continue;                                   // warp-uniform
+                const long long g = chunk * UNROLL + u;
+                const long long idx = g * 32 + lane;
+                bool claim = false;
+                if ((m[u] >> lane) & 1u) {
+                    const float d = mahalanobis<E>(x[u], c, b);             // clusterers.py:129-130
+                    if (d <= a.d1) {                                        // clusterers.py:136-143
+                        claim = true;
+                        a.primary[idx] = i;
+                    } else {
+                        const unsigned long long k = make_key(sd[u], static_cast<unsigned int>(idx));
+                        key = k > key ? k : key;
+                    }
+                }
+                const unsigned int claimed = __ballot_sync(0xffffffffu, claim);
+                if (claimed != 0u && lane == 0) a.avail[g] = m[u] & ~claimed;
+            }
+        }
+        if (i + 1 < a.max_inst) {
+            publish_key<THREADS>(key, a.best + i + 1, s_red);
+            ++generation;
+            grid_barrier(a.barrier, generation);
+        }
+    }
+
+    // Secondary assignment (clusterers.py:148-159); see seq_cluster_kernel for the stale-mask rule
+    const bool exhausted = exit_reason == 0;
+    const bool do_secondary = num_clusters >= 1 && exit_reason != 1;
+    for (long long idx = tid0; idx < n; idx += stride) {
+        const int pl = a.primary[idx];
+        long long out = pl < 0 ? -1ll : static_cast<long long>(pl) + a.label_start;
+        const bool avail = pl < 0 || (exhausted && pl == a.max_inst - 1);
+        if (do_secondary && avail) {
+            float x[E];
+            load_point<E, VEC>(a.emb, idx, x);
+            float dmax = 0.f;
+            int kmax = 0;
+            bool has_nan = false;
+            for (int k = 0; k < num_clusters; ++k) {
+                const float d = mahalanobis<E>(x, s_center[k], s_bw[k]);
+                has_nan |= (d != d);
+                if (k == 0 || d > dmax) { dmax = d; kmax = k; }                // first max wins (clusterers.py:153)
+            }
+            if (!has_nan && dmax <= a.d2) out = static_cast<long long>(kmax) + a.label_start;
+        }
+        a.labels[idx] = out;
+    }
+
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            a.meta[0] = static_cast<unsigned int>(num_clusters);
+            a.meta[1] = static_cast<unsigned int>(exit_reason);
+            a.meta[2] = static_cast<unsigned int>(n);
+            a.meta[3] = 0u;
+        }
+        float* centers = reinterpret_cast<float*>(a.meta + 4 + a.max_inst);
+        float* bws = centers + static_cast<size_t>(a.max_inst) * E;
+        for (int q = threadIdx.x; q < num_clusters * E; q += THREADS) {
+            centers[q] = s_center[q / E][q % E];
+            bws[q] = s_bw[q / E][q % E];
+        }
+    }
+}
+
+template <int E, bool VEC, int THREADS, int UNROLL>
+int launch_cluster_stream(const ClusterArgs& args, cudaStream_t stream) {
+    auto kernel = seq_cluster_stream_kernel<E, VEC, THREADS, UNROLL>;
+    int per_sm = 0;
+    SS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0));
+    if (per_sm < 1) {
+        set_error("seq_cluster: streaming kernel does not fit on an SM");
+        return STEMSEG_ERR_CUDA;
+    }
+    long long blocks = static_cast<long long>(per_sm) * device_sm_count();
+    const long long useful = (args.n + 32ll * UNROLL * (THREADS / 32) - 1) / (32ll * UNROLL * (THREADS / 32));
+    if (blocks > useful) blocks = useful;
+    void* kargs[] = {const_cast<ClusterArgs*>(&args)};
+    SS_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(static_cast<unsigned>(blocks)),
+                                           dim3(THREADS), kargs, 0, stream));
+    return STEMSEG_OK;
+}
+
+// STEMSEG_CLUSTER_STREAM = "legacy" | "<threads>x<unroll>" (256x4, 256x8, 512x4, 512x8); default below
+int stream_variant() {
+    static int v = -1;
+    if (v >= 0) return v;
+    const char* e = getenv("STEMSEG_CLUSTER_STREAM");
+    v = 1;                                              // default: 256 threads x 4 groups
+    if (e != nullptr) {
+        if (!strcmp(e, "legacy")) v = 0;
+        else if (!strcmp(e, "256x4")) v = 1;
+        else if (!strcmp(e, "256x8")) v = 2;
+        else if (!strcmp(e, "512x4")) v = 3;
+        else if (!strcmp(e, "512x8")) v = 4;
+        else if (!strcmp(e, "256x2")) v = 5;
+    }
+    return v;
+}
+
 template <int E, bool VEC, int R>
 int launch_cluster_r(const ClusterArgs& args, long long blocks, cudaStream_t stream) {
     auto kernel = seq_cluster_kernel<E, VEC, R>;
@@ -350,6 +542,14 @@ int launch_cluster(const ClusterArgs& args, cudaStream_t stream) {
     if (blocks_for(2) <= resident_blocks<E, VEC, 2>()) return launch_cluster_r<E, VEC, 2>(args, blocks_for(2), stream);
     if (blocks_for(1) <= resident_blocks<E, VEC, 1>()) return launch_cluster_r<E, VEC, 1>(args, blocks_for(1), stream);
     // streaming variant: fill the device
+    switch (stream_variant()) {
+        case 1: return launch_cluster_stream<E, VEC, 256, 4>(args, stream);
+        case 2: return launch_cluster_stream<E, VEC, 256, 8>(args, stream);
+        case 3: return launch_cluster_stream<E, VEC, 512, 4>(args, stream);
+        case 4: return launch_cluster_stream<E, VEC, 512, 8>(args, stream);
+        case 5: return launch_cluster_stream<E, VEC, 256, 2>(args, stream);
+        default: break;
+    }
     long long blocks = resident_blocks<E, VEC, 0>();
     if (blocks < 1) {
         set_error("seq_cluster: kernel does not fit on an SM");
@@ -369,6 +569,10 @@ int launch_cluster_e(const ClusterArgs& args, bool vec, cudaStream_t stream) {
 
 using namespace stemseg;
 
+static size_t cluster_fixed_ws_bytes(int max_instances) {
+    return align_up(sizeof(unsigned long long) * (max_instances + 1) + sizeof(unsigned int), 256);
+}
+
 extern "C" size_t stemseg_seq_cluster_meta_words(int32_t e, int32_t max_instances) {
     return 4 + static_cast<size_t>(max_instances) * (1 + 2 * static_cast<size_t>(e));
 }
@@ -377,7 +581,7 @@ extern "C" int32_t stemseg_seq_cluster_workspace_bytes(const StemsegClusterParam
     SS_REQUIRE(p != nullptr && bytes != nullptr, "seq_cluster_workspace_bytes: null argument");
     SS_REQUIRE(p->max_instances >= 0 && p->max_instances <= kMaxI, "max_instances %d out of range [0,%d]",
                p->max_instances, kMaxI);
-    *bytes = align_up(sizeof(unsigned long long) * (p->max_instances + 1) + sizeof(unsigned int), 256);
+    *bytes = cluster_fixed_ws_bytes(p->max_instances) + align_up(sizeof(unsigned int) * ((p->n_points + 31) / 32 + 8), 256);
     return STEMSEG_OK;
 }
 
@@ -437,7 +641,8 @@ extern "C" int32_t stemseg_seq_cluster(const float* embeddings, const float* ban
     a.meta = static_cast<unsigned int*>(meta);
     a.best = static_cast<unsigned long long*>(workspace);
     a.barrier = reinterpret_cast<unsigned int*>(a.best + p->max_instances + 1);
-    SS_CUDA_OK(cudaMemsetAsync(workspace, 0, need, stream));
+    a.avail = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + cluster_fixed_ws_bytes(p->max_instances));
+    SS_CUDA_OK(cudaMemsetAsync(workspace, 0, cluster_fixed_ws_bytes(p->max_instances), stream));
 
     const bool vec = (reinterpret_cast<uintptr_t>(embeddings) % 16u) == 0;
     switch (p->embedding_dims) {

@@ -20,9 +20,19 @@ __device__ __forceinline__ void sgd_update(float& p, float g, float& buf, float 
     p = __fsub_rn(p, __fmul_rn(lr, step));
 }
 
+// hyper: optional device array {lr, momentum, weight_decay, grad_scale}; when given it overrides the by-value arguments,
+// so that a CUDA graph that captured this launch follows a learning-rate schedule (the reference steps its scheduler
+// every iteration, stemseg/training/main.py:209-210) without being re-captured
 __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ param, const float* __restrict__ grad,
                                                            float* __restrict__ buf, long long n, float lr, float momentum,
-                                                           float wd, float grad_scale, int nesterov) {
+                                                           float wd, float grad_scale, int nesterov,
+                                                           const float* __restrict__ hyper) {
+    if (hyper != nullptr) {
+        lr = __ldg(hyper + 0);
+        momentum = __ldg(hyper + 1);
+        wd = __ldg(hyper + 2);
+        grad_scale = __ldg(hyper + 3);
+    }
     const long long stride = 1ll * gridDim.x * blockDim.x;
     const long long n4 = n / 4;
     float4* p4 = reinterpret_cast<float4*>(param);
@@ -47,9 +57,23 @@ __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* __restrict__ p
 
 using namespace stemseg;
 
+static int32_t sgd_step_impl(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                             float weight_decay, float grad_scale, int32_t nesterov, const float* hyper, void* stream_);
+
 extern "C" int32_t stemseg_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
                                     float momentum, float weight_decay, float grad_scale, int32_t nesterov,
                                     void* stream_) {
+    return sgd_step_impl(param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, nesterov, nullptr, stream_);
+}
+
+extern "C" int32_t stemseg_sgd_step_dev(float* param, const float* grad, float* momentum_buf, int64_t n,
+                                        const float* hyper, int32_t nesterov, void* stream_) {
+    SS_REQUIRE(hyper != nullptr, "sgd_step_dev: null hyper-parameter array");
+    return sgd_step_impl(param, grad, momentum_buf, n, 0.f, 0.f, 0.f, 1.f, nesterov, hyper, stream_);
+}
+
+static int32_t sgd_step_impl(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                             float weight_decay, float grad_scale, int32_t nesterov, const float* hyper, void* stream_) {
     SS_REQUIRE(param && grad && momentum_buf && n >= 0, "sgd_step: bad arguments");
     SS_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                  reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0,
@@ -61,7 +85,7 @@ extern "C" int32_t stemseg_sgd_step(float* param, const float* grad, float* mome
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     sgd_nesterov_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(param, grad, momentum_buf, n, lr, momentum,
-                                                                           weight_decay, grad_scale, nesterov);
+                                                                           weight_decay, grad_scale, nesterov, hyper);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
 }

@@ -387,7 +387,7 @@ class HeadSet(object):
             convs = [s.weights.stages[name][0][0] for s in self.specs]
             groups = first_stage_groups([c.cout for c in convs])
             self.first_stage[name] = [(_fuse_rows([convs[i] for i in g]), g) for g in groups]
-        self._entries = {}
+        self._entries = _lib.LRUCache(4)      # captured plans per input shape (each owns a private graph pool)
 
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
     def _branch(self, name, n_stages, a_in, trace):
@@ -500,7 +500,7 @@ class HeadSet(object):
         with torch.cuda.device(dev):
             if entry is None:
                 entry = self._capture(feats_32_16_8_4, dev)
-                self._entries[key] = entry
+                self._entries.put(key, entry)
             for f, pl in zip(feats_32_16_8_4, entry["in_planes"]):
                 pack_activation(f, self.planes, out=pl)
             entry["graph"].replay()

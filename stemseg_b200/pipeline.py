@@ -79,6 +79,7 @@ class SubclipPipeline(object):
         self.fuse_heads = True          # run all heads as one HeadSet (shared im2col operand, one CUDA graph)
         self.use_step_graph = True      # heads + compaction + gather + clustering replayed as one CUDA graph
         self.steps_in_flight = 2        # independent graph instances used round-robin by submit()
+        self.max_cached_shapes = 4      # captured step graphs kept per instance (LRU; older shapes are re-captured)
         self._group = None
         self._group_key = None
 
@@ -210,7 +211,8 @@ class SubclipPipeline(object):
             raise ValueError("SubclipPipeline processes one sub-clip at a time (batch dimension must be 1)")
         dev = emb_in[0].device
         if not hasattr(self, "_step_graphs"):
-            self._step_graphs = {}
+            # bounded: each entry owns a CUDA graph with a private pool of ~1-3 GB (keyed on shapes / weights version)
+            self._step_graphs = _lib.LRUCache(self.max_cached_shapes * max(1, self.steps_in_flight))
             self._instance = 0
         # `steps_in_flight` independent instances (own static buffers, own stream) are used round-robin, so the
         # latency-bound tail of step i (merges, clustering) overlaps the convolutions of step i+1
@@ -221,8 +223,9 @@ class SubclipPipeline(object):
         with torch.cuda.device(dev):
             entry = self._step_graphs.get(key)
             if entry is None:
-                entry = self._step_graphs[key] = self._capture_step(emb_in, fg_mask)
+                entry = self._capture_step(emb_in, fg_mask)
                 entry["stream"] = torch.cuda.Stream(device=dev)
+                self._step_graphs.put(key, entry)
             caller = torch.cuda.current_stream(dev)
             run_stream = entry["stream"] if self.steps_in_flight > 1 else caller
             if run_stream is not caller:

@@ -30,6 +30,7 @@ import torch
 import torch.distributed as dist
 
 from stemseg_b200 import _lib
+from stemseg_b200._lib import LRUCache
 
 
 class FlatParameters(object):
@@ -60,6 +61,13 @@ class FlatParameters(object):
                 p.data = view
                 p.grad = self.grad[off:off + p.numel()].view_as(p)
         self.offsets = offsets
+        # gradients of block_32x / block_16x (complete early in the backward pass) form a contiguous prefix
+        names = [n for n, p in module.named_parameters() if p.requires_grad]
+        self.prefix_end = total
+        for n, off in zip(names, offsets):
+            if n.startswith("block_8x."):
+                self.prefix_end = off
+                break
 
     def zero_grad(self):
         self.grad.zero_()
@@ -125,6 +133,15 @@ def sgd_step(flat, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
                                         1 if nesterov else 0, _lib.stream_ptr()))
 
 
+def sgd_step_dev(flat, hyper, nesterov):
+    """Same pass with {lr, momentum, weight_decay, grad_scale} read from the device array `hyper` (float32 [4]) when the
+    kernel runs -- the form captured into CUDA graphs, so that schedules keep working after capture."""
+    lib = _lib.load()
+    with torch.cuda.device(flat.data.device):
+        _lib.check(lib.stemseg_sgd_step_dev(_lib.ptr(flat.data), _lib.ptr(flat.grad), _lib.ptr(flat.momentum), flat.numel,
+                                            _lib.ptr(hyper), 1 if nesterov else 0, _lib.stream_ptr()))
+
+
 class DecoderTrainer(object):
     """forward -> loss -> backward -> gradient exchange -> SGD for the decoder heads, one sub-clip per rank per step.
 
@@ -134,21 +151,26 @@ class DecoderTrainer(object):
     defaults.yaml:17-34."""
 
     def __init__(self, heads, criterion, lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True, group=None,
-                 use_graph=True, need_feature_grads=True, overlap_heads=True, weight_semseg=1.0):
+                 use_graph=True, need_feature_grads=True, overlap_heads=True, weight_semseg=1.0, max_cached_shapes=4):
         self.use_graph = use_graph
         # graph mode with two heads: run the heads' forward (and, after the loss, their backward) concurrently on two
         # streams inside ONE graph -- the latency-bound small kernels of one head hide under the tensor-core
         # convolutions of the other.  False: three graphs, per-head all-reduce overlapped with the other head's backward.
         self.overlap_heads = overlap_heads
+        # data-parallel runs: cut the backward pass in two graphs so that the all-reduce of the low-resolution blocks'
+        # gradients (81 % of the bytes, complete after a small part of the backward time) overlaps block_8x / block_4x
+        self.split_backward = None            # None = automatically when world > 1
         self.need_feature_grads = need_feature_grads
         self.group = group
-        self._graphs = {}
         self.embedding_head = heads["embedding"]
         self.seediness_head = heads.get("seediness")
         self.semseg_head = heads.get("semseg")
         self.weight_semseg = float(weight_semseg)            # cfg.TRAINING.LOSSES.WEIGHT_SEMSEG (defaults.yaml:34)
         self.criterion = criterion
         self.lr, self.momentum, self.weight_decay, self.nesterov = lr, momentum, weight_decay, nesterov
+        self._graphs = LRUCache(max_cached_shapes)
+        self._hyper = None                    # device float32 [4] read by the captured SGD launches
+        self._hyper_values = None
         mods = self._modules()
         for m in mods:
             m.train()
@@ -158,6 +180,22 @@ class DecoderTrainer(object):
         if self.world > 1:      # identical starting point on every rank, like DistributedDataParallel's constructor
             for flat in self.flats:
                 dist.broadcast(flat.data, src=0, group=group)
+
+    def set_lr(self, lr):
+        """Learning rate of the next step (the reference calls lr_scheduler.step() every iteration,
+        training/main.py:209-210).  Takes effect in graph mode too: the captured SGD launches read it from device memory."""
+        self.lr = float(lr)
+
+    def _sync_hyper(self, device):
+        """Upload {lr, momentum, weight_decay, 1/world} if they changed since the last step (tiny async H2D copy)."""
+        values = (float(self.lr), float(self.momentum), float(self.weight_decay), 1.0 / self.world)
+        if self._hyper is None:
+            self._hyper = torch.empty(4, dtype=torch.float32, device=device)
+        if values != self._hyper_values:
+            # pageable source: the 16 bytes are staged by the driver before the call returns, and stream order makes
+            # the device-side write wait for the previous step's SGD launch that may still be reading the array
+            self._hyper.copy_(torch.tensor(values, dtype=torch.float32), non_blocking=True)
+            self._hyper_values = values
 
     def forward_loss(self, feats_32_16_8_4, targets):
         """TrainingModel.forward after the backbone (model_builder.py:107-126) through torch autograd."""
@@ -205,6 +243,7 @@ class DecoderTrainer(object):
         from stemseg_b200.losses import embedding_loss_and_gradient
         mods, flats = self._modules(), self.flats
         state = {}
+        split = (self.world > 1) if self.split_backward is None else bool(self.split_backward)
 
         def seg_forward_loss_backward_last():
             saved, outs = [], []
@@ -237,7 +276,7 @@ class DecoderTrainer(object):
 
         def seg_optimizer():
             for flat in flats:
-                sgd_step(flat, self.lr, self.momentum, self.weight_decay, self.nesterov, 1.0 / self.world)
+                sgd_step_dev(flat, self._hyper, self.nesterov)       # hyper-parameters from device memory (set_lr)
 
         def seg_heads_concurrently():
             """Every head on its own stream: forward, join, losses + gradients on the main stream, fork, backward."""
@@ -281,13 +320,43 @@ class DecoderTrainer(object):
                     cls_view, fg, entry["semseg_ids"], entry["ignore"], self.weight_semseg, 1.0, grad_out=g_sem[0])
                 grads_out.append(g_sem)
             state["grads_out"], state["saved"], state["outs"] = grads_out, saved, outs
+            if split:
+                carries = [None] * len(mods)
+                fork()
+                for k in reversed(range(len(mods))):
+                    with torch.cuda.stream(streams[k]):
+                        carries[k], _ = A.training_backward(mods[k], saved[k], grads_out[k],
+                                                            grad_dst=self._grad_slots(flats[k]),
+                                                            need_feature_grads=self.need_feature_grads, phase="early")
+                join()
+                state["carries"] = carries
+                return
+            backward_rest(None)
+
+        def backward_rest(carries):
+            main = torch.cuda.current_stream()
+            sides = entry["side_streams"][:len(mods) - 1]
+            streams = [main] + sides
             fgs = [None] * len(mods)
-            fork()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for st in sides:
+                st.wait_event(ev)
             for k in reversed(range(len(mods))):
                 with torch.cuda.stream(streams[k]):
-                    fgs[k], _ = A.training_backward(mods[k], saved[k], grads_out[k], grad_dst=self._grad_slots(flats[k]),
-                                                    need_feature_grads=self.need_feature_grads)
-            join()
+                    if carries is None:
+                        fgs[k], _ = A.training_backward(mods[k], state["saved"][k], state["grads_out"][k],
+                                                        grad_dst=self._grad_slots(flats[k]),
+                                                        need_feature_grads=self.need_feature_grads)
+                    else:
+                        fgs[k], _ = A.training_backward(mods[k], state["saved"][k], state["grads_out"][k],
+                                                        grad_dst=self._grad_slots(flats[k]),
+                                                        need_feature_grads=self.need_feature_grads, phase="late",
+                                                        carry=carries[k])
+            for st in sides:
+                ev2 = torch.cuda.Event()
+                ev2.record(st)
+                main.wait_event(ev2)
             state["fg"] = fgs
             total = None
             if self.need_feature_grads:                       # every head reads the same pyramid
@@ -296,8 +365,16 @@ class DecoderTrainer(object):
                     total = [a + b for a, b in zip(total, other)]
             entry["feature_grads"] = total
 
+        def seg_late_backward():
+            backward_rest(state["carries"])
+
         if len(mods) >= 2 and (self.overlap_heads or self.semseg_head is not None):
+            if split:
+                entry["mode"] = "concurrent_split"
+                return [seg_heads_concurrently, seg_late_backward, seg_optimizer]
+            entry["mode"] = "concurrent"
             return [seg_heads_concurrently, seg_optimizer]
+        entry["mode"] = "serial"
         return [seg_forward_loss_backward_last, seg_backward_first, seg_optimizer]
 
     def _capture(self, feats, targets):
@@ -343,10 +420,11 @@ class DecoderTrainer(object):
         key = (tuple(tuple(f.shape) for f in feats), tuple(masks.shape), str(feats[0].device))
         dev = feats[0].device
         with torch.no_grad(), torch.cuda.device(dev):
+            self._sync_hyper(dev)
             entry = self._graphs.get(key)
             if entry is None:
                 entry = self._capture(feats, targets)
-                self._graphs[key] = entry
+                self._graphs.put(key, entry)
             planes = D.PRECISION_PLANES[self.embedding_head.precision]
             for f, pl in zip(feats, entry["in_planes"]):
                 D.pack_activation(f.detach(), planes, out=pl)
@@ -356,10 +434,21 @@ class DecoderTrainer(object):
                 entry["semseg_ids"].copy_(targets[0]["semseg_masks"], non_blocking=True)
             pending = []
             graphs = entry["graphs"]
-            if len(graphs) == 2:               # both heads in one graph, then both reductions
+            if entry["mode"] == "concurrent":  # both heads in one graph, then both reductions
                 graphs[0][0].replay()
                 if self.world > 1:
                     pending = [dist.all_reduce(f.grad, group=self.group, async_op=True) for f in self.flats]
+            elif entry["mode"] == "concurrent_split":
+                # forward + loss + early backward | reduce the low-resolution blocks' gradients while the long
+                # block_8x / block_4x backward runs | reduce the rest
+                graphs[0][0].replay()
+                if self.world > 1:
+                    pending = [dist.all_reduce(f.grad[:f.prefix_end], group=self.group, async_op=True)
+                               for f in self.flats]
+                graphs[1][0].replay()
+                if self.world > 1:
+                    pending += [dist.all_reduce(f.grad[f.prefix_end:], group=self.group, async_op=True)
+                                for f in self.flats if f.prefix_end < f.numel]
             else:
                 graphs[0][0].replay()
                 if self.world > 1:             # gradients of the last head are complete: reduce while g2 runs
