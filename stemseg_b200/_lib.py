@@ -267,6 +267,9 @@ class LRUCache(object):
         while len(self._d) > self.capacity:
             self._d.popitem(last=False)              # dropping the entry releases its graphs and their pool
 
+    def clear(self):
+        self._d.clear()
+
     def __len__(self):
         return len(self._d)
 

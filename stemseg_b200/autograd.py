@@ -47,7 +47,7 @@ def training_forward(head, feats, in_planes=None):
     """Eager forward keeping what the backward needs.  Returns (out, saved).
 
     in_planes: the four feature maps already packed (D.pack_activation), e.g. static buffers shared by several heads."""
-    spec = head.head_spec()
+    spec = head.head_spec(exact=True)
     weights, out_spec = spec.weights, spec.out_spec
     planes = D.PRECISION_PLANES[head.precision]
     pools, tscale = D.pool_schedule(head.num_frames)

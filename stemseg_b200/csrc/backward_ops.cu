@@ -11,6 +11,7 @@
 #include "trilinear.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace stemseg {
 namespace {
@@ -545,6 +546,13 @@ __global__ void __launch_bounds__(256) to_planes_kernel(const float* __restrict_
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
         const float v[4] = {a.x, a.y, a.z, a.w};
         __nv_bfloat16 hi[4], lo[4];
+        if (planes == STEMSEG_PLANES_FP16) {                 // one fp16 plane (same 2-byte storage)
+            __half hh[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hh[k] = __float2half_rn(v[k]);
+            *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<uint2*>(hh);
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) split_bf16_b(v[k], hi[k], lo[k]);
         *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<uint2*>(hi);
@@ -836,7 +844,7 @@ extern "C" int32_t stemseg_channel_sum(const float* x, int64_t rows, int32_t c, 
 
 extern "C" int32_t stemseg_to_planes(const float* x, int64_t elems, void* dst_planes, int32_t planes, void* stream_) {
     SS_REQUIRE(x && dst_planes && elems >= 4 && elems % 4 == 0, "to_planes: bad arguments");
-    SS_REQUIRE(planes == 1 || planes == 2, "to_planes: planes must be 1 or 2");
+    SS_REQUIRE(planes == 1 || planes == 2 || planes == STEMSEG_PLANES_FP16, "to_planes: planes must be 1, 2 or STEMSEG_PLANES_FP16");
     SS_REQUIRE(al16(x) && al16(dst_planes), "to_planes: alignment");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     to_planes_kernel<<<grid_cap(elems / 4, 256), 256, 0, stream>>>(x, elems / 4, static_cast<__nv_bfloat16*>(dst_planes),

@@ -54,6 +54,7 @@ struct ConvTcParams {
                                // so that a long layer is a stream of short-lived CTAs and higher-priority kernels of
                                // other graph branches get SMs while it runs
     int num_stages;            // smem pipeline depth
+    int operand_fp16;          // 1: the (single) operand planes hold fp16 instead of bf16 values
     float* stat_partial;       // optional [n][cout][tiles_per_sample][2]: per-tile (sum, sum of squares) of every output
                                // channel, consumed by gn_finalize (GroupNorm statistics without re-reading the output)
     int tiles_per_sample;
@@ -182,6 +183,11 @@ template <int N>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+// same with A and B as F16 (format code 0 in both operand fields)
+template <int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
 }
 
 // Column sums over the 32 rows held by a warp: v[i] is this lane's (row's) value of column i.  Butterfly
@@ -342,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+        const uint32_t idesc = p.operand_fp16 ? make_idesc_f16<BLOCK_N>() : make_idesc<BLOCK_N>();
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -918,7 +924,9 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
                            float* stat_partial, const StemsegConvShape* s, int32_t max_ctas, void* stream_,
                            const ConvTcParams* head) {
     SS_REQUIRE(s != nullptr && act_planes && weight_planes && (out || head), "conv3d: null pointer");
-    SS_REQUIRE(s->planes == 1 || s->planes == 2, "conv3d: planes must be 1 or 2");
+    SS_REQUIRE(s->planes == 1 || s->planes == 2 || s->planes == STEMSEG_PLANES_FP16,
+               "conv3d: planes must be 1, 2 or STEMSEG_PLANES_FP16");
+    const int plane_count = s->planes == 2 ? 2 : 1;
     SS_REQUIRE(s->kernel_size == 3 || s->kernel_size == 1, "conv3d: kernel_size must be 1 or 3");
     SS_REQUIRE(s->n >= 1 && s->t >= 1 && s->h >= 1 && s->w >= 1, "conv3d: empty volume");
     SS_REQUIRE(s->cin >= 32 && s->cin % 32 == 0, "conv3d: cin must be a positive multiple of 32 (got %d)", s->cin);
@@ -950,6 +958,7 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     p.out = out;
     p.bias = bias;
     p.num_stages = 0;
+    p.operand_fp16 = s->planes == STEMSEG_PLANES_FP16 ? 1 : 0;
     p.wgrad_mode = 0;
     p.k_splits = 1;
     p.k_chunks_total = 0;
@@ -973,7 +982,7 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
 
     // BLOCK_K: 64 channels (SWIZZLE_128B) when the stage still leaves >= 3 pipeline stages, else 32 (SWIZZLE_64B)
     int block_k = (s->cin % 64 == 0) ? 64 : 32;
-    if (block_k == 64 && s->planes == 2 && block_n == 256) block_k = 32;
+    if (block_k == 64 && plane_count == 2 && block_n == 256) block_k = 32;
 
     const size_t act_plane_bytes = static_cast<size_t>(p.n) * p.t * p.h * p.w * p.cin * 2;
     const int64_t k_total = static_cast<int64_t>(p.ntaps) * p.cin;
@@ -982,13 +991,13 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     const uint8_t* a = static_cast<const uint8_t*>(act_planes);
     const uint8_t* b = static_cast<const uint8_t*>(weight_planes);
     for (int pl = 0; pl < 2; ++pl) {
-        const int src = pl < s->planes ? pl : 0;
+        const int src = pl < plane_count ? pl : 0;
         rc = encode_act_map(&maps[pl], a + src * act_plane_bytes, p, block_k);
         if (rc != STEMSEG_OK) return rc;
         rc = encode_weight_map(&maps[2 + pl], b + src * w_plane_bytes, k_total, p.cout, block_k, block_n);
         if (rc != STEMSEG_OK) return rc;
     }
-    if (s->planes == 2)
+    if (plane_count == 2)
         return block_k == 64 ? launch_by_n<64, 2>(block_n, maps, p, max_ctas, stream)
                              : launch_by_n<32, 2>(block_n, maps, p, max_ctas, stream);
     return block_k == 64 ? launch_by_n<64, 1>(block_n, maps, p, max_ctas, stream)
@@ -1219,6 +1228,7 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
     p.slice_stride = static_cast<size_t>(cout) * cin;
     p.k_splits = k_splits;
     p.wgrad_mode = 1;
+    p.operand_fp16 = 0;
     const int hp = h + 2 * pad, pitch = pad ? (w + 2 + 7) / 8 * 8 : w;
     const int shifts = kernel_size == 3 ? 3 : 1;
     for (int tap = 0; tap < 27; ++tap) {

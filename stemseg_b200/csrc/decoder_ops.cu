@@ -7,9 +7,19 @@
 #include "trilinear.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace stemseg {
 namespace {
+
+constexpr int kPlanesFp16 = STEMSEG_PLANES_FP16;     // one fp16 plane stored in the bf16-typed buffer (same 2 bytes)
+__host__ __device__ __forceinline__ bool valid_planes(int planes, bool allow_fp16) {
+    return planes == 1 || planes == 2 || (allow_fp16 && planes == kPlanesFp16);
+}
+__device__ __forceinline__ __nv_bfloat16 half_bits_as_bf16(float x) {
+    const __half h = __float2half_rn(x);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
 
 // ---- fp32 -> bf16 planes: x ~= hi + lo (lo = bf16(x - hi)), round-to-nearest-even both times ------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -24,6 +34,12 @@ struct alignas(8) bf16x4 {
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi_plane, size_t plane_elems, int planes, size_t off,
                                               const float (&x)[4]) {
     bf16x4 h, l;
+    if (planes == kPlanesFp16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h.v[k] = half_bits_as_bf16(x[k]);
+        *reinterpret_cast<bf16x4*>(hi_plane + off) = h;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) split_bf16(x[k], h.v[k], l.v[k]);
     *reinterpret_cast<bf16x4*>(hi_plane + off) = h;
@@ -58,6 +74,12 @@ __global__ void __launch_bounds__(256) pack_ncthw_kernel(const float* __restrict
         if (s < hw && cc < c) {
             const size_t off = ((static_cast<size_t>(nt) * hw + s) * c) + cc;
             __nv_bfloat16 h0, l0, h1, l1;
+            if (planes == kPlanesFp16) {
+                h0 = half_bits_as_bf16(tile[2 * tx][ty + 8 * i]);
+                h1 = half_bits_as_bf16(tile[2 * tx + 1][ty + 8 * i]);
+                *reinterpret_cast<__nv_bfloat162*>(dst + off) = __nv_bfloat162(h0, h1);
+                continue;
+            }
             split_bf16(tile[2 * tx][ty + 8 * i], h0, l0);
             split_bf16(tile[2 * tx + 1][ty + 8 * i], h1, l1);
             *reinterpret_cast<__nv_bfloat162*>(dst + off) = __nv_bfloat162(h0, h1);
@@ -81,7 +103,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int cout, int 
         __nv_bfloat16 h, l;
         split_bf16(x, h, l);
         const size_t off = (static_cast<size_t>(row_begin + co) * taps + tap) * cin_count + ci;
-        dst[off] = h;
+        dst[off] = planes == kPlanesFp16 ? half_bits_as_bf16(x) : h;
         if (planes == 2) dst[plane_elems + off] = l;
     }
 }
@@ -570,7 +592,7 @@ extern "C" int32_t stemseg_pack_activation(const float* src, int64_t stride_n, i
                                            int32_t n, int32_t c, int32_t t, int32_t hw, void* dst_planes,
                                            int32_t planes, void* stream_) {
     SS_REQUIRE(src && dst_planes, "pack_activation: null pointer");
-    SS_REQUIRE(planes == 1 || planes == 2, "pack_activation: planes must be 1 or 2");
+    SS_REQUIRE(valid_planes(planes, true), "pack_activation: planes must be 1, 2 or STEMSEG_PLANES_FP16");
     SS_REQUIRE(n >= 1 && c >= 2 && c % 2 == 0 && t >= 1 && hw >= 1, "pack_activation: bad shape");
     SS_REQUIRE(1ll * n * t <= 65535, "pack_activation: n*t too large");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -586,7 +608,7 @@ extern "C" int32_t stemseg_pack_conv_weight(const float* src, int32_t cout, int3
                                             int32_t cin_count, int32_t taps, void* dst_planes, int32_t row_begin,
                                             int32_t rows_total, int32_t planes, void* stream_) {
     SS_REQUIRE(src && dst_planes, "pack_conv_weight: null pointer");
-    SS_REQUIRE(planes == 1 || planes == 2, "pack_conv_weight: planes must be 1 or 2");
+    SS_REQUIRE(valid_planes(planes, true), "pack_conv_weight: planes must be 1, 2 or STEMSEG_PLANES_FP16");
     SS_REQUIRE(cout >= 1 && cin_count >= 1 && cin_begin >= 0 && cin_begin + cin_count <= cin_total && taps >= 1 &&
                    row_begin >= 0 && row_begin + cout <= rows_total,
                "pack_conv_weight: bad shape");
@@ -683,7 +705,7 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
                                           int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool,
                                           void* dst_planes, int32_t planes, void* stream_) {
     SS_REQUIRE(x && dst_planes, "norm_relu_pool: null pointer");
-    SS_REQUIRE(planes == 1 || planes == 2, "norm_relu_pool: planes must be 1 or 2");
+    SS_REQUIRE(valid_planes(planes, true), "norm_relu_pool: planes must be 1, 2 or STEMSEG_PLANES_FP16");
     SS_REQUIRE(slices >= 1 && slices <= 27, "norm_relu_pool: slices out of range");
     SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "norm_relu_pool: bad row stride");
     SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");

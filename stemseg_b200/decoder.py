@@ -29,6 +29,25 @@ ACT_IDENTITY, ACT_TANH_QUARTER, ACT_SIGMOID = 0, 1, 2
 COORD_NONE, COORD_T, COORD_Y, COORD_X = 0, 1, 2, 3
 
 PRECISION_PLANES = {"fp32": 2, "bf16": 1}
+PLANES_FP16 = 17        # include/stemseg_b200.h STEMSEG_PLANES_FP16: one fp16 plane, one tensor-core product per MAC
+
+# fp32-parity mode: scale blocks whose 3x3x3 convolutions run as ONE fp16 product per MAC instead of three bf16 products.
+# profiles/r02_precision_ablation.json (scripts/precision_ablation.py): block_8x + block_16x in fp16 keep the worst output
+# channel at 2.6-4.5e-5 of the 1e-4 budget over three seeds (all-bf16x3: 0.7-1.1e-5); the 4x layer and the 1x1 merges need the
+# three products (2-4e-4 otherwise), block_32x is 3.6 % of the MACs and stays exact to keep the margin above 2x.
+import os as _os
+FP32_FAST_BLOCKS = tuple(b for b in _os.environ.get("STEMSEG_FP32_FAST_BLOCKS", "block_8x,block_16x").split(",") if b)
+
+
+def plane_count(planes):
+    return 2 if planes == 2 else 1
+
+
+def block_planes(planes, block_name, exact=False):
+    """Operand format of the 3x3x3 convolutions of one scale block under head precision `planes`."""
+    if planes == 2 and not exact and block_name in FP32_FAST_BLOCKS:
+        return PLANES_FP16
+    return planes
 
 # bench.py sets this to a list to collect (shape, start_event, end_event) around every conv launch
 PROFILE_EVENTS = None
@@ -44,8 +63,9 @@ def pool_schedule(num_frames):
 class PackedConv(object):
     """Weights of one convolution in kernel layout: bf16 planes [P][rows][taps*cin] (+ fp32 bias)."""
 
-    def __init__(self, planes_tensor, bias, cin, cout, kernel_size):
+    def __init__(self, planes_tensor, bias, cin, cout, kernel_size, planes=None):
         self.planes_tensor, self.bias, self.cin, self.cout, self.kernel_size = planes_tensor, bias, cin, cout, kernel_size
+        self.planes = planes_tensor.shape[0] if planes is None else planes        # format code (1, 2 or PLANES_FP16)
 
 
 def _check(rc):
@@ -65,22 +85,24 @@ def pack_conv_weight(weight, planes, cin_begin=0, cin_count=None, bias=None):
         raise NotImplementedError("only 1x1x1 and 3x3x3 convolutions are on the path (got %s)" % (tuple(w.shape),))
     cin_count = cin_total - cin_begin if cin_count is None else cin_count
     with torch.cuda.device(w.device):
-        dst = torch.empty((planes, cout, taps * cin_count), dtype=torch.bfloat16, device=w.device)
+        dst = torch.empty((plane_count(planes), cout, taps * cin_count), dtype=torch.bfloat16, device=w.device)
         _check(lib.stemseg_pack_conv_weight(_lib.ptr(w), cout, cin_total, cin_begin, cin_count, taps, _lib.ptr(dst), 0,
                                             cout, planes, _lib.stream_ptr()))
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-    return PackedConv(dst, b, cin_count, cout, 3 if taps == 27 else 1)
+    return PackedConv(dst, b, cin_count, cout, 3 if taps == 27 else 1, planes)
 
 
 class Planes(object):
     """An NDHWC activation stored as bf16 planes [P][n][t][h][w][c]."""
 
-    def __init__(self, tensor, n, t, h, w, c):
+    def __init__(self, tensor, n, t, h, w, c, planes=None):
         self.tensor, self.n, self.t, self.h, self.w, self.c = tensor, n, t, h, w, c
+        self._planes = tensor.shape[0] if planes is None else planes
 
     @property
     def planes(self):
-        return self.tensor.shape[0]
+        """Format code: 1 (bf16), 2 (bf16 hi + lo) or PLANES_FP16 (one fp16 plane in the same 2-byte storage)."""
+        return self._planes
 
 
 def pack_activation(x, planes, out=None):
@@ -100,18 +122,19 @@ def pack_activation(x, planes, out=None):
         x = x.contiguous()
     with torch.cuda.device(x.device):
         if out is not None:
-            if tuple(out.tensor.shape) != (planes, n, t, h, w, c) or out.tensor.device != x.device:
+            if tuple(out.tensor.shape) != (plane_count(planes), n, t, h, w, c) or out.tensor.device != x.device or \
+                    out.planes != planes:
                 raise ValueError("pack_activation: static buffer %s does not match input %s" % (
-                    tuple(out.tensor.shape), (planes, n, t, h, w, c)))
+                    tuple(out.tensor.shape), (plane_count(planes), n, t, h, w, c)))
             dst = out.tensor
         else:
-            dst = torch.empty((planes, n, t, h, w, c), dtype=torch.bfloat16, device=x.device)
+            dst = torch.empty((plane_count(planes), n, t, h, w, c), dtype=torch.bfloat16, device=x.device)
         if ndhwc:
             _check(lib.stemseg_to_planes(_lib.ptr(x), n * c * t * h * w, _lib.ptr(dst), planes, _lib.stream_ptr()))
         else:
             _check(lib.stemseg_pack_activation(_lib.ptr(x), x.stride(0), x.stride(1), x.stride(2), n, c, t, h * w,
                                                _lib.ptr(dst), planes, _lib.stream_ptr()))
-    return Planes(dst, n, t, h, w, c)
+    return Planes(dst, n, t, h, w, c, planes)
 
 
 # conv launches with at least this many tiles per SM run as short-lived CTAs (CHUNK_TILES consecutive tiles each)
@@ -128,8 +151,8 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked
     lib = _lib.load()
     if act.c != packed.cin:
         raise ValueError("conv input has %d channels, weights expect %d" % (act.c, packed.cin))
-    if act.planes != packed.planes_tensor.shape[0]:
-        raise ValueError("activation / weight precision mismatch")
+    if act.planes != packed.planes:
+        raise ValueError("activation / weight precision mismatch (%s vs %s)" % (act.planes, packed.planes))
     shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes,
                                   1, 0)
     if chunked:
@@ -204,12 +227,12 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
                 KEEP.extend((ws, scale_shift))
             slices = 1                               # the statistics pass summed the split-K slices into slice 0
         t_out = (t - 1) // 2 + 1 if pool else t
-        dst = torch.empty((planes, n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
+        dst = torch.empty((plane_count(planes), n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
         _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c,
                                           1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
     if saved is not None:
         saved["scale_shift"], saved["mean_rstd"] = scale_shift, mean_rstd_out
-    return Planes(dst, n, t_out, h, w, c)
+    return Planes(dst, n, t_out, h, w, c, planes)
 
 
 def upsample_add(z, y_low, t_scale, planes):
@@ -298,13 +321,14 @@ def fused_merge_head_output(act, packed, y_low, t_scale, spec, max_ctas=0):
 class TrunkWeights(object):
     """Kernel-layout weights of one head: per block a list of (PackedConv, gamma, beta); per merge (W_a, W_b)."""
 
-    def __init__(self, state, inter_channels, planes, has_norm):
+    def __init__(self, state, inter_channels, planes, has_norm, exact=False):
         self.inter_channels = list(inter_channels)
+        self.planes, self.exact = planes, exact
         self.stages = {}
         for name, n_stages in BLOCKS:
             lst = []
             for j in range(n_stages):
-                conv = pack_conv_weight(state["%s.%d.weight" % (name, 4 * j)], planes,
+                conv = pack_conv_weight(state["%s.%d.weight" % (name, 4 * j)], block_planes(planes, name, exact),
                                         bias=state["%s.%d.bias" % (name, 4 * j)])
                 gamma = beta = None
                 if has_norm:
@@ -336,7 +360,7 @@ def _fuse_rows(convs):
     bias = None
     if first.bias is not None:
         bias = torch.cat([c.bias for c in convs], dim=0).contiguous()
-    return PackedConv(planes_tensor, bias, first.cin, sum(c.cout for c in convs), first.kernel_size)
+    return PackedConv(planes_tensor, bias, first.cin, sum(c.cout for c in convs), first.kernel_size, first.planes)
 
 
 def first_stage_groups(couts):
@@ -408,8 +432,10 @@ class HeadSet(object):
             if trace is not None and hi == trace[0]:
                 full = y.sum(0) if y.dim() == 6 else y.clone()
                 trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
+            # operands of the block's later stages use the block's format; its last output feeds a merge (head format)
+            fmt = block_planes(self.planes, name)
             a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
-                                     self.pools[0] and name != "block_4x", self.planes,
+                                     self.pools[0] and name != "block_4x", fmt if n_stages > 1 else self.planes,
                                      channel_slice=(c0, conv.cout), stat=stat)
             KEEP.append(a.tensor)
             for j in range(1, n_stages):
@@ -419,8 +445,8 @@ class HeadSet(object):
                 KEEP.extend((yj, statj))
                 if trace is not None and hi == trace[0]:
                     trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj.clone()
-                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j], self.planes,
-                                         stat=statj)
+                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j],
+                                         fmt if j + 1 < n_stages else self.planes, stat=statj)
                 KEEP.append(a.tensor)
             outs.append(a)
         return outs
@@ -492,7 +518,7 @@ class HeadSet(object):
         if trace is not None or not self.use_graph:
             KEEP = []
             with torch.cuda.device(dev):
-                in_planes = [pack_activation(f, self.planes) for f in feats_32_16_8_4]
+                in_planes = self.pack_inputs(feats_32_16_8_4)
                 outs = self._plan(in_planes, trace=trace)
             KEEP = []
             return outs
@@ -501,15 +527,19 @@ class HeadSet(object):
             if entry is None:
                 entry = self._capture(feats_32_16_8_4, dev)
                 self._entries.put(key, entry)
-            for f, pl in zip(feats_32_16_8_4, entry["in_planes"]):
-                pack_activation(f, self.planes, out=pl)
+            self.pack_inputs(feats_32_16_8_4, out=entry["in_planes"])
             entry["graph"].replay()
             _lib.KERNEL_LAUNCHES[0] += entry["kernels"]
             return [o.clone() for o in entry["outputs"]]
 
+    def pack_inputs(self, feats_32_16_8_4, out=None):
+        """D0: the four feature maps -> operand planes in the format of the scale block that reads them."""
+        return [pack_activation(f, block_planes(self.planes, name), out=None if out is None else out[b])
+                for b, ((name, _), f) in enumerate(zip(BLOCKS, feats_32_16_8_4))]
+
     def _capture(self, feats, dev):
         global KEEP
-        in_planes = [pack_activation(f, self.planes) for f in feats]
+        in_planes = self.pack_inputs(feats)
         # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, ...) before capturing
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())

@@ -99,9 +99,21 @@ class _SqueezeExpandTrunk(nn.Module):
     def _output_spec(self, state):
         raise NotImplementedError
 
-    def head_spec(self):
-        """Kernel-layout weights of this head (repacked when a parameter changes); shared with linked HeadSets."""
+    def head_spec(self, exact=False):
+        """Kernel-layout weights of this head (repacked when a parameter changes); shared with linked HeadSets.
+
+        exact=True (training): every convolution in the head's nominal operand format; the inference plan may run
+        block_8x / block_16x with single fp16 operands in fp32-parity mode (decoder.FP32_FAST_BLOCKS)."""
         key = self._cache_key()
+        if exact:
+            cached = getattr(self, "_packed_exact", None)
+            if cached is None or cached[0] != key:
+                state = self._trunk_state()
+                planes = D.PRECISION_PLANES[self.precision]
+                weights = D.TrunkWeights(state, self.inter_channels, planes, self._has_norm, exact=True)
+                cached = (key, D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps))
+                self._packed_exact = cached
+            return cached[1]
         if self._packed is None or self._packed_key != key:
             state = self._trunk_state()
             planes = D.PRECISION_PLANES[self.precision]
@@ -125,6 +137,7 @@ class _SqueezeExpandTrunk(nn.Module):
         """Call after modifying parameters behind autograd's back (e.g. the fused optimiser kernel writes the flat
         buffer the parameters are views of): the next forward / backward repacks the kernel-layout weights."""
         self._packed = self._packed_key = self._head_set = None
+        self._packed_exact = None
         self._dgrad_cache = None
 
     def _get_head_set(self):

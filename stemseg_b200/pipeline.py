@@ -154,7 +154,7 @@ class SubclipPipeline(object):
         group = self._head_group()
         dev = emb_in[0].device
         e, v = self.embedding_head.embedding_size, self.embedding_head.variance_channels
-        in_planes = [D.pack_activation(f, group.planes) for f in emb_in]
+        in_planes = group.pack_inputs(emb_in)
         mask_static = None if fg_mask is None else torch.empty_like(fg_mask)
         if mask_static is not None:
             mask_static.copy_(fg_mask)
@@ -232,8 +232,7 @@ class SubclipPipeline(object):
                 run_stream.wait_stream(caller)                  # the caller's features / mask are ready
             stream_ctx = torch.cuda.stream(run_stream)
             stream_ctx.__enter__()
-            for f, pl in zip(emb_in, entry["in_planes"]):
-                D.pack_activation(f, entry["planes"], out=pl)
+            self._head_group().pack_inputs(emb_in, out=entry["in_planes"])
             if fg_mask is not None:
                 entry["mask"].copy_(fg_mask)
             consumed = torch.cuda.Event()
