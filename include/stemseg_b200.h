@@ -225,8 +225,9 @@ int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample
                                     const float* gamma, const float* beta, float* scale_shift, float* mean_rstd,
                                     void* stream);
 
-/* relu(x * scale + shift) [-> AvgPool3d(3, stride=(2,1,1), padding=1), divisor 27] -> bf16 planes
- * (embedding_decoder.py:22-24; common.py:8-24).  scale_shift NULL = no normalisation (NormType Identity). */
+/* relu(x * scale + shift) [-> pooling] -> operand planes (embedding_decoder.py:22-24; common.py:8-24).
+ * pool: 0 none, 1 AvgPool3d(3, stride=(2,1,1), padding=1) with divisor 27 (cfg POOL_TYPE "avg"), 2 MaxPool3d with the
+ * same window (POOL_TYPE "max", model_builder.py:28-30).  scale_shift NULL = no normalisation (NormType Identity). */
 int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift, int32_t n,
                                int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool, void* dst_planes,
                                int32_t planes, void* stream);

@@ -34,7 +34,7 @@ OFFSET_CHANNELS = {"xy": "yx", "ff": "", "xyt": "tyx", "xyf": "yx", "xytf": "tyx
                    "xyfff": "yx"}
 
 
-def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None, relu_masks=None):
+def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None, relu_masks=None, pool_type="avg"):
     """conv3x3x3(pad 1) -> GroupNorm -> ReLU -> [AvgPool3d(3, (2,1,1), 1)]   (embedding_decoder.py:21-24).
 
     relu_masks (gradient tests only): {"<block>.<conv_idx>": 0/1 tensor} replaces the ReLU's own sign decision by a
@@ -52,14 +52,16 @@ def conv_stage(x, sd, prefix, conv_idx, gn_groups, pooled, trace=None, relu_mask
         y = y * relu_masks[key].to(y.dtype)
     else:
         y = F.relu(y)
-    if pooled:
+    if pooled and pool_type == "max":                             # POOLER_REGISTRY "max" (model_builder.py:28-30)
+        y = F.max_pool3d(y, 3, stride=(2, 1, 1), padding=1)
+    elif pooled:
         y = F.avg_pool3d(y, 3, stride=(2, 1, 1), padding=1)      # count_include_pad=True -> always /27
     if trace is not None:
         trace["%s.%d.out" % (prefix, conv_idx)] = y
     return y
 
 
-def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None, relu_masks=None):
+def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None, relu_masks=None, pool_type="avg"):
     """Shared trunk of all three heads -> [N, c3, T, H/4, W/4] (embedding_decoder.py:109-129)."""
     pools = POOL_SLOTS[num_frames]
     tscale = TEMPORAL_SCALES[num_frames]
@@ -68,7 +70,7 @@ def trunk(sd, feats_32_16_8_4, num_frames, gn_groups=32, trace=None, relu_masks=
         y = f
         for j in range(stages):
             y = conv_stage(y, sd, name, 4 * j, gn_groups, pools[j] and name not in UNPOOLED_BLOCKS, trace,
-                           relu_masks)    # Sequential indices 0,4,8
+                           relu_masks, pool_type)    # Sequential indices 0,4,8
         branch.append(y)
     x = branch[0]
     for k, merge in enumerate(MERGES):
@@ -91,9 +93,9 @@ def coordinate_grid(t, h, w, time_scale=1.0):
 
 
 def embedding_head(sd, feats, num_frames, embedding_size, dim_mode, tanh_activation=True, seediness_output=True,
-                   gn_groups=32, trace=None, relu_masks=None):
+                   gn_groups=32, trace=None, relu_masks=None, pool_type="avg"):
     """-> cat(embeddings, variances[, seediness]) [N, E + (E - free) + {0,1}, T, H/4, W/4]."""
-    x = trunk(sd, feats, num_frames, gn_groups, trace, relu_masks)
+    x = trunk(sd, feats, num_frames, gn_groups, trace, relu_masks, pool_type)
     emb = F.conv3d(x, sd["conv_embedding.weight"], None)
     assert emb.shape[1] == EMBEDDING_DIMS[dim_mode] == embedding_size
     if tanh_activation:
@@ -112,14 +114,15 @@ def embedding_head(sd, feats, num_frames, embedding_size, dim_mode, tanh_activat
     return torch.cat(outs, dim=1)
 
 
-def seediness_head(sd, feats, num_frames, gn_groups=32, trace=None, relu_masks=None):
-    return F.conv3d(trunk(sd, feats, num_frames, gn_groups, trace, relu_masks), sd["conv_out.weight"], None).sigmoid()
+def seediness_head(sd, feats, num_frames, gn_groups=32, trace=None, relu_masks=None, pool_type="avg"):
+    return F.conv3d(trunk(sd, feats, num_frames, gn_groups, trace, relu_masks, pool_type), sd["conv_out.weight"],
+                    None).sigmoid()
 
 
-def semseg_head(sd, feats_4_8_16_32, num_frames, gn_groups=32, trace=None, relu_masks=None):
+def semseg_head(sd, feats_4_8_16_32, num_frames, gn_groups=32, trace=None, relu_masks=None, pool_type="avg"):
     """Input list arrives highest resolution first and is reversed (semseg_decoder.py:94)."""
-    return F.conv3d(trunk(sd, feats_4_8_16_32[::-1], num_frames, gn_groups, trace, relu_masks), sd["conv_out.weight"],
-                    None)
+    return F.conv3d(trunk(sd, feats_4_8_16_32[::-1], num_frames, gn_groups, trace, relu_masks, pool_type),
+                    sd["conv_out.weight"], None)
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -349,4 +349,11 @@ class HeadFunction(torch.autograd.Function):
 
 def run_head_with_grad(head, feats_32_16_8_4):
     params = [p for _, p in head.named_parameters()]
-    return HeadFunction.apply(head, len(feats_32_16_8_4), *feats_32_16_8_4, *params)
+    n = feats_32_16_8_4[0].shape[0]
+    if n == 1:
+        return HeadFunction.apply(head, len(feats_32_16_8_4), *feats_32_16_8_4, *params)
+    # batch > 1 (embedding_decoder.py:101-145 accepts any N): every op of the head is per sample (GroupNorm statistics
+    # included), so the batch is a loop of single-sample nodes whose parameter gradients autograd accumulates
+    outs = [HeadFunction.apply(head, len(feats_32_16_8_4), *[f[i:i + 1] for f in feats_32_16_8_4], *params)
+            for i in range(n)]
+    return torch.cat(outs, dim=0)

@@ -344,8 +344,6 @@ __global__ void __launch_bounds__(THREADS) seq_cluster_stream_kernel(const Clust
     const long long total_warps = static_cast<long long>(gridDim.x) * (THREADS / 32);
     const long long n_groups = (n + 31) / 32;
     const long long n_chunks = (n_groups + UNROLL - 1) / UNROLL;
-    const long long tid0 = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
 
     {   // pass 0: everything unassigned (clusterers.py:96); winner of iteration 0
         unsigned long long key = 0ull;
@@ -435,10 +433,16 @@ __global__ void __launch_bounds__(THREADS) seq_cluster_stream_kernel(const Clust
         }
     }
 
-    // Secondary assignment (clusterers.py:148-159); see seq_cluster_kernel for the stale-mask rule
+    // Secondary assignment (clusterers.py:148-159); see seq_cluster_kernel for the stale-mask rule.  Same chunk -> warp
+    // mapping as the iterations: a thread only reads `primary` entries it wrote itself (the last iteration is not
+    // followed by a grid barrier, so claims made there are not yet visible to other threads).
     const bool exhausted = exit_reason == 0;
     const bool do_secondary = num_clusters >= 1 && exit_reason != 1;
-    for (long long idx = tid0; idx < n; idx += stride) {
+    for (long long chunk = warp_global; chunk < n_chunks; chunk += total_warps)
+#pragma unroll 1
+    for (int u = 0; u < UNROLL; ++u) {
+        const long long idx = (chunk * UNROLL + u) * 32 + lane;
+        if (idx >= n) continue;
         const int pl = a.primary[idx];
         long long out = pl < 0 ? -1ll : static_cast<long long>(pl) + a.label_start;
         const bool avail = pl < 0 || (exhausted && pl == a.max_inst - 1);
@@ -492,19 +496,16 @@ int launch_cluster_stream(const ClusterArgs& args, cudaStream_t stream) {
     return STEMSEG_OK;
 }
 
-// STEMSEG_CLUSTER_STREAM = "legacy" | "<threads>x<unroll>" (256x4, 256x8, 512x4, 512x8); default below
+// STEMSEG_CLUSTER_STREAM = "legacy" | "256x4" | "256x8" overrides the per-E choice made in launch_cluster
 int stream_variant() {
-    static int v = -1;
-    if (v >= 0) return v;
+    static int v = -2;
+    if (v != -2) return v;
     const char* e = getenv("STEMSEG_CLUSTER_STREAM");
-    v = 1;                                              // default: 256 threads x 4 groups
+    v = -1;                                             // -1: choose by embedding size (launch_cluster)
     if (e != nullptr) {
         if (!strcmp(e, "legacy")) v = 0;
         else if (!strcmp(e, "256x4")) v = 1;
         else if (!strcmp(e, "256x8")) v = 2;
-        else if (!strcmp(e, "512x4")) v = 3;
-        else if (!strcmp(e, "512x8")) v = 4;
-        else if (!strcmp(e, "256x2")) v = 5;
     }
     return v;
 }
@@ -541,13 +542,14 @@ int launch_cluster(const ClusterArgs& args, cudaStream_t stream) {
     if (blocks_for(4) <= resident_blocks<E, VEC, 4>()) return launch_cluster_r<E, VEC, 4>(args, blocks_for(4), stream);
     if (blocks_for(2) <= resident_blocks<E, VEC, 2>()) return launch_cluster_r<E, VEC, 2>(args, blocks_for(2), stream);
     if (blocks_for(1) <= resident_blocks<E, VEC, 1>()) return launch_cluster_r<E, VEC, 1>(args, blocks_for(1), stream);
-    // streaming variant: fill the device
-    switch (stream_variant()) {
+    // streaming variant: fill the device.  Measured on B200 (profiles/r02_cluster_variants.txt): with >= 32 bytes of
+    // embedding per point the bit-mask kernel with 8 groups in flight per warp wins (E=8, N=6.6M: 1.37 ms vs 1.71 ms);
+    // with 16-byte points the state-array kernel below is faster (E=4, N=3.3M: 0.44 ms vs 0.50 ms)
+    int variant = stream_variant();
+    if (variant < 0) variant = E >= 6 ? 2 : 0;
+    switch (variant) {
         case 1: return launch_cluster_stream<E, VEC, 256, 4>(args, stream);
         case 2: return launch_cluster_stream<E, VEC, 256, 8>(args, stream);
-        case 3: return launch_cluster_stream<E, VEC, 512, 4>(args, stream);
-        case 4: return launch_cluster_stream<E, VEC, 512, 8>(args, stream);
-        case 5: return launch_cluster_stream<E, VEC, 256, 2>(args, stream);
         default: break;
     }
     long long blocks = resident_blocks<E, VEC, 0>();

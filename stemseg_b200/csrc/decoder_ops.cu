@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(512) gn_finalize_kernel(const float* __restric
 // K2c: y = relu((x - mean) * rstd * gamma + beta) [-> AvgPool3d(3, stride (2,1,1), pad 1, divisor 27)] -> bf16 planes
 // Replaces GroupNorm apply + ReLU + AvgPool3d (embedding_decoder.py:22-24; common.py:8-24).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool POOL>
+// POOL: 0 = none, 1 = AvgPool3d(3, stride (2,1,1), padding 1) (zero padding counted: always /27), 2 = MaxPool3d with the
+// same window (padding never wins: the pooled values are post-ReLU, >= 0, and every window holds a real voxel)
+template <int POOL>
 __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
                                                            int n, int t, int h, int w, int c, int t_out,
                                                            int row_stride, int slices, size_t slice_stride,
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
             sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (POOL) {
+        if (POOL != 0) {
             for (int dt = -1; dt <= 1; ++dt) {
                 const int ti = 2 * to + dt;
                 if (ti < 0 || ti >= t) continue;
@@ -281,15 +283,21 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
                         const float4 a = load_sum_slices(
                             reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + ti) * h + hi) * w + wi) * row_stride) + q,
                             slice_stride / 4, slices);
-                        acc[0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
-                        acc[1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
-                        acc[2] += fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
-                        acc[3] += fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                        const float v0 = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f), v1 = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+                        const float v2 = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f), v3 = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                        if (POOL == 2) {
+                            acc[0] = fmaxf(acc[0], v0); acc[1] = fmaxf(acc[1], v1);
+                            acc[2] = fmaxf(acc[2], v2); acc[3] = fmaxf(acc[3], v3);
+                        } else {
+                            acc[0] += v0; acc[1] += v1; acc[2] += v2; acc[3] += v3;
+                        }
                     }
                 }
             }
+            if (POOL == 1) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] *= (1.0f / 27.0f);
+                for (int k = 0; k < 4; ++k) acc[k] *= (1.0f / 27.0f);
+            }
         } else {
             const float4 a = load_sum_slices(
                 reinterpret_cast<const float4*>(x + (((static_cast<size_t>(nn) * t + to) * h + hh) * w + ww) * row_stride) + q,
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
 // (t,h)-summed columns are shared between neighbouring outputs (54 loads per 4 outputs instead of 108).
 constexpr int kPoolW = 4;
 
+template <bool MAXPOOL>
 __global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
                                                               int n, int t, int h, int w, int c, int t_out, int row_stride,
                                                               __nv_bfloat16* __restrict__ dst, size_t plane_elems,
@@ -345,10 +354,14 @@ __global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __res
                     const int wi = w0 + k - 1;
                     if (wi < 0 || wi >= w) continue;
                     const float4 a = __ldg(reinterpret_cast<const float4*>(rowp + static_cast<size_t>(wi) * row_stride) + q);
-                    col[k][0] += fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
-                    col[k][1] += fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
-                    col[k][2] += fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
-                    col[k][3] += fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                    const float v0 = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f), v1 = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+                    const float v2 = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f), v3 = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+                    if (MAXPOOL) {
+                        col[k][0] = fmaxf(col[k][0], v0); col[k][1] = fmaxf(col[k][1], v1);
+                        col[k][2] = fmaxf(col[k][2], v2); col[k][3] = fmaxf(col[k][3], v3);
+                    } else {
+                        col[k][0] += v0; col[k][1] += v1; col[k][2] += v2; col[k][3] += v3;
+                    }
                 }
             }
         }
@@ -358,7 +371,9 @@ __global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __res
             if (wo >= w) break;
             float r[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = (col[k][e] + col[k + 1][e] + col[k + 2][e]) * (1.0f / 27.0f);
+            for (int e = 0; e < 4; ++e)
+                r[e] = MAXPOOL ? fmaxf(fmaxf(col[k][e], col[k + 1][e]), col[k + 2][e])
+                               : (col[k][e] + col[k + 1][e] + col[k + 2][e]) * (1.0f / 27.0f);
             const size_t off = ((((static_cast<size_t>(nn) * t_out + to) * h + hh) * w + wo) * c) + 4 * q;
             store_planes4(dst, plane_elems, planes, off, r);
         }
@@ -707,6 +722,7 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     SS_REQUIRE(x && dst_planes, "norm_relu_pool: null pointer");
     SS_REQUIRE(valid_planes(planes, true), "norm_relu_pool: planes must be 1, 2 or STEMSEG_PLANES_FP16");
     SS_REQUIRE(slices >= 1 && slices <= 27, "norm_relu_pool: slices out of range");
+    SS_REQUIRE(pool >= 0 && pool <= 2, "norm_relu_pool: pool must be 0 (none), 1 (average) or 2 (max)");
     SS_REQUIRE(row_stride >= c && row_stride % 4 == 0, "norm_relu_pool: bad row stride");
     SS_REQUIRE(n >= 1 && t >= 1 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "norm_relu_pool: bad shape");
     SS_REQUIRE(aligned16(x) && aligned16(dst_planes) && aligned16(scale_shift),
@@ -717,17 +733,23 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     const size_t slice_stride = static_cast<size_t>(n) * t * h * w * row_stride;
     const long long total = 1ll * n * t_out * h * w * (c / 4);
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
-    if (pool && slices == 1)
-        gn_relu_pool_w4_kernel<<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
+    if (pool == 1 && slices == 1)
+        gn_relu_pool_w4_kernel<false><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
-    else if (pool)
-        gn_relu_pool_kernel<true><<<grid_for(total, 256, 16), 256, 0, stream>>>(
+    else if (pool == 2 && slices == 1)
+        gn_relu_pool_w4_kernel<true><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
+            x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
+    else if (pool == 1)
+        gn_relu_pool_kernel<1><<<grid_for(total, 256, 16), 256, 0, stream>>>(
+            x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
+    else if (pool == 2)
+        gn_relu_pool_kernel<2><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     else if (slices == 1)
         gn_relu_flat_kernel<<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
             x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, row_stride / 4, total, dst, plane_elems, planes);
     else
-        gn_relu_pool_kernel<false><<<grid_for(total, 256, 16), 256, 0, stream>>>(
+        gn_relu_pool_kernel<0><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;

@@ -188,6 +188,9 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked
     return out
 
 
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+
+
 def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_slice=None, stat=None,
                          saved=None):
     """fp32 NDHWC conv output ([split_k,] n,t,h,w,c_total) -> relu(GN(y)) [-> avgpool] as Planes.
@@ -229,7 +232,7 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((plane_count(planes), n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
         _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c,
-                                          1 if pool else 0, _lib.ptr(dst), planes, _lib.stream_ptr()))
+                                          int(pool), _lib.ptr(dst), planes, _lib.stream_ptr()))      # True == POOL_AVG
     if saved is not None:
         saved["scale_shift"], saved["mean_rstd"] = scale_shift, mean_rstd_out
     return Planes(dst, n, t_out, h, w, c, planes)
@@ -347,8 +350,9 @@ class TrunkWeights(object):
 class HeadSpec(object):
     """Everything the plan needs to know about one head."""
 
-    def __init__(self, weights, out_spec, num_groups, eps):
+    def __init__(self, weights, out_spec, num_groups, eps, pool_mode=POOL_AVG):
         self.weights, self.out_spec, self.num_groups, self.eps = weights, out_spec, num_groups, eps
+        self.pool_mode = pool_mode             # POOL_AVG / POOL_MAX for the slots that pool (cfg POOL_TYPE)
 
 
 def _fuse_rows(convs):
@@ -414,8 +418,11 @@ class HeadSet(object):
         self._entries = _lib.LRUCache(4)      # captured plans per input shape (each owns a private graph pool)
 
     # ---- the plan itself (eager or under capture) -----------------------------------------------------------
-    def _branch(self, name, n_stages, a_in, trace):
-        """All conv stages of one scale block for every head; returns per-head Planes."""
+    def _branch(self, name, n_stages, a_in, trace, post_stream=None):
+        """All conv stages of one scale block for every head; returns per-head Planes.
+
+        post_stream: stream (high priority) that takes over after the first-stage convolution -- used for block_4x,
+        whose long GEMM stays on the normal-priority main stream while everything after it is latency-bound."""
         first = {}                                   # head index -> (conv output, statistics, channel offset)
         for fused, members in self.first_stage[name]:
             res = conv3d(a_in, fused, allow_split=True, want_stats=self.fuse_stats, chunked=self.chunk_long_layers)
@@ -425,6 +432,13 @@ class HeadSet(object):
             for hi in members:
                 first[hi] = (y, stat, c0)
                 c0 += self.specs[hi].weights.stages[name][0][0].cout
+        if post_stream is not None:
+            post_stream.wait_event(torch.cuda.current_stream().record_event())
+            with torch.cuda.stream(post_stream):
+                return self._branch_tail(name, n_stages, first, trace)
+        return self._branch_tail(name, n_stages, first, trace)
+
+    def _branch_tail(self, name, n_stages, first, trace):
         outs = []
         for hi, spec in enumerate(self.specs):
             conv, gamma, beta = spec.weights.stages[name][0]
@@ -435,8 +449,8 @@ class HeadSet(object):
             # operands of the block's later stages use the block's format; its last output feeds a merge (head format)
             fmt = block_planes(self.planes, name)
             a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
-                                     self.pools[0] and name != "block_4x", fmt if n_stages > 1 else self.planes,
-                                     channel_slice=(c0, conv.cout), stat=stat)
+                                     spec.pool_mode if (self.pools[0] and name != "block_4x") else POOL_NONE,
+                                     fmt if n_stages > 1 else self.planes, channel_slice=(c0, conv.cout), stat=stat)
             KEEP.append(a.tensor)
             for j in range(1, n_stages):
                 conv, gamma, beta = spec.weights.stages[name][j]
@@ -445,7 +459,8 @@ class HeadSet(object):
                 KEEP.extend((yj, statj))
                 if trace is not None and hi == trace[0]:
                     trace[1]["%s.%d.conv" % (name, 4 * j)] = yj.sum(0) if yj.dim() == 6 else yj.clone()
-                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps, self.pools[j],
+                a = group_norm_relu_pool(yj, gamma, beta, spec.num_groups, spec.eps,
+                                         spec.pool_mode if self.pools[j] else POOL_NONE,
                                          fmt if j + 1 < n_stages else self.planes, stat=statj)
                 KEEP.append(a.tensor)
             outs.append(a)
@@ -453,20 +468,39 @@ class HeadSet(object):
 
     def _plan(self, in_planes, trace=None, streams=None):
         main = torch.cuda.current_stream()
+        self._tail_stream = None
         branches = [None] * 4
         if streams is None:
             for b, (name, n_stages) in enumerate(BLOCKS):
                 branches[b] = self._branch(name, n_stages, in_planes[b], trace)
         else:
+            # Priorities (two steps are in flight on two graph instances, pipeline.SubclipPipeline.submit): only the
+            # long first-stage GEMM of block_4x runs at normal priority on `main`; the three small scale branches and
+            # EVERYTHING after the 4x GEMM (GroupNorm apply, merges, output heads and -- in the step graph -- compaction,
+            # gather, clustering) run on high-priority streams.  Otherwise the block scheduler serves the other step's
+            # 4x GEMM (thousands of queued CTAs, launched earlier) before this step's small tail kernels, and the two
+            # steps run in lock-step: conv phase, conv phase, both tails (profiles/r02_timeline_cfg3_before.txt).
+            tail = streams[3] if len(streams) > 3 else None
             fork = main.record_event()
             for b, (name, n_stages) in enumerate(BLOCKS):
                 st = main if b == 3 else streams[b]
                 if st is not main:
                     st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    branches[b] = self._branch(name, n_stages, in_planes[b], trace)
+                    branches[b] = self._branch(name, n_stages, in_planes[b], trace,
+                                               post_stream=tail if (b == 3 and tail is not None) else None)
+            if tail is not None:
+                for b in range(3):
+                    tail.wait_event(streams[b].record_event())
+                with torch.cuda.stream(tail):
+                    outs = self._merge_all(branches, trace, tail, streams[:3])
+                self._tail_stream = tail               # the caller continues the step on it and joins `main` at the end
+                return outs
             for b in range(3):
                 main.wait_event(streams[b].record_event())
+        return self._merge_all(branches, trace, main, streams)
+
+    def _merge_all(self, branches, trace, main, streams):
         def merge_chain(hi, spec):
             x = branches[0][hi]
             out = None
@@ -550,11 +584,14 @@ class HeadSet(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]     # small branches: high priority
+        # high priority: the three small scale branches + the tail after the 4x GEMM (see _plan)
+        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(4)]
         KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]
         with _lib.capture_guard(), torch.cuda.graph(graph):
             outputs = self._plan(in_planes, streams=streams)
+            if self._tail_stream is not None:        # join the capture's origin stream
+                torch.cuda.current_stream().wait_event(self._tail_stream.record_event())
         kernels = _lib.KERNEL_LAUNCHES[0] - before
         keep, KEEP = KEEP, []
         return {"graph": graph, "in_planes": in_planes, "outputs": outputs, "keep": keep, "kernels": kernels,

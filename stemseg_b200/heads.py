@@ -50,8 +50,9 @@ class _SqueezeExpandTrunk(nn.Module):
 
     def __init__(self, in_channels, inter_channels, PoolType, NormType, num_frames, precision):
         super().__init__()
-        if PoolType is not nn.AvgPool3d:
-            raise NotImplementedError("only PoolType=nn.AvgPool3d (cfg POOL_TYPE 'avg') has a CUDA path")
+        if PoolType not in (nn.AvgPool3d, nn.MaxPool3d):                           # model_builder.py:28-30
+            raise NotImplementedError("PoolType must be nn.AvgPool3d or nn.MaxPool3d (cfg POOL_TYPE 'avg' / 'max')")
+        self._pool_mode = D.POOL_MAX if PoolType is nn.MaxPool3d else D.POOL_AVG
         if precision not in D.PRECISION_PLANES:
             raise ValueError("precision must be 'fp32' (bf16x2 split, 1e-4 parity) or 'bf16'")
         self.num_frames = _resolve_num_frames(num_frames)
@@ -61,7 +62,7 @@ class _SqueezeExpandTrunk(nn.Module):
         self.inter_channels = list(inter_channels)
 
         def stage(cin, cout, slot, pooled_block=True):
-            pool = nn.AvgPool3d(3, stride=(2, 1, 1), padding=1) if (pooled_block and self._pools[slot]) else nn.Identity()
+            pool = PoolType(3, stride=(2, 1, 1), padding=1) if (pooled_block and self._pools[slot]) else nn.Identity()
             mods = [nn.Conv3d(cin, cout, 3, stride=1, padding=1), NormType(cout), nn.ReLU(inplace=True)]
             return mods + ([pool] if pooled_block else [])
 
@@ -111,14 +112,14 @@ class _SqueezeExpandTrunk(nn.Module):
                 state = self._trunk_state()
                 planes = D.PRECISION_PLANES[self.precision]
                 weights = D.TrunkWeights(state, self.inter_channels, planes, self._has_norm, exact=True)
-                cached = (key, D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps))
+                cached = (key, D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps, self._pool_mode))
                 self._packed_exact = cached
             return cached[1]
         if self._packed is None or self._packed_key != key:
             state = self._trunk_state()
             planes = D.PRECISION_PLANES[self.precision]
             weights = D.TrunkWeights(state, self.inter_channels, planes, self._has_norm)
-            self._packed = D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps)
+            self._packed = D.HeadSpec(weights, self._output_spec(state), self._num_groups, self._eps, self._pool_mode)
             self._packed_key = key
             self._head_set = None
         return self._packed
@@ -156,6 +157,9 @@ class _SqueezeExpandTrunk(nn.Module):
                                                   any(f.requires_grad for f in feats_32_16_8_4))
         if needs_grad:
             # training: eager CUDA forward that keeps its intermediates + hand-written backward (autograd.py)
+            if self._pool_mode != D.POOL_AVG:
+                raise NotImplementedError("training through the B200 heads supports POOL_TYPE 'avg' (every shipped "
+                                          "config); 'max' is available for inference (torch.no_grad())")
             from stemseg_b200.autograd import run_head_with_grad
             return run_head_with_grad(self, feats_32_16_8_4)
         with torch.no_grad():

@@ -161,6 +161,16 @@ class SubclipPipeline(object):
 
         def body(streams):
             outs = [o.squeeze(0) for o in group._plan(in_planes, streams=streams)]
+            tail = group._tail_stream if streams is not None else None
+            if tail is None:
+                return rest(outs)
+            # everything after the long 4x GEMM stays on the plan's high-priority tail stream (decoder.HeadSet._plan)
+            with torch.cuda.stream(tail):
+                state = rest(outs)
+            torch.cuda.current_stream().wait_event(tail.record_event())
+            return state
+
+        def rest(outs):
             out = outs.pop(0)
             seediness = out[e + v:e + v + 1] if self.embedding_head.seediness_channels else outs.pop(0)
             semseg = outs.pop(0) if self.semseg_head is not None else None
@@ -187,7 +197,7 @@ class SubclipPipeline(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]     # small branches: high priority
+        streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(4)]     # small branches + tail: high priority
         from stemseg_b200 import _lib
         D.KEEP = []
         before = _lib.KERNEL_LAUNCHES[0]

@@ -24,6 +24,16 @@ def case_table():
                                  h4=24, w4=32, embedding_size=4, dim_mode="xyff", tanh=True, seediness_output=False)
     c["seediness_fullwidth_t8"] = dict(kind="seediness", in_channels=256, inter=[256, 256, 128, 128], num_frames=8,
                                        n=1, h4=24, w4=32)
+    # NUM_FRAMES 24 / 32 (three pooling slots like 16, common.py:22-23,34-35) and POOL_TYPE "max" (model_builder.py:30)
+    c["emb_xyff_t24"] = dict(kind="embedding", in_channels=32, inter=[32, 32, 32, 32], num_frames=24, n=1, h4=24,
+                             w4=24, embedding_size=4, dim_mode="xyff", tanh=True, seediness_output=True)
+    c["seediness_t32"] = dict(kind="seediness", in_channels=32, inter=[32, 32, 32, 32], num_frames=32, n=1, h4=24,
+                              w4=24)
+    c["emb_xyff_maxpool_t8"] = dict(kind="embedding", in_channels=64, inter=[64, 64, 32, 32], num_frames=8, n=1,
+                                    h4=24, w4=32, embedding_size=4, dim_mode="xyff", tanh=True, seediness_output=True,
+                                    pool="max")
+    c["semseg_4_maxpool_t16"] = dict(kind="semseg", in_channels=32, inter=[32, 32, 32, 32], num_frames=16, n=1, h4=24,
+                                     w4=24, num_out=4, pool="max")
     return c
 
 
@@ -49,9 +59,10 @@ def build_case(name):
 def run_oracle(name, trace=None):
     from oracle import decoder_oracle as do
     sd, feats, case = build_case(name)
+    pool = case.get("pool", "avg")
     if case["kind"] == "embedding":
         return do.embedding_head(sd, feats, case["num_frames"], case["embedding_size"], case["dim_mode"],
-                                 case["tanh"], case["seediness_output"], trace=trace)
+                                 case["tanh"], case["seediness_output"], trace=trace, pool_type=pool)
     if case["kind"] == "seediness":
-        return do.seediness_head(sd, feats, case["num_frames"], trace=trace)
-    return do.semseg_head(sd, feats, case["num_frames"], trace=trace)
+        return do.seediness_head(sd, feats, case["num_frames"], trace=trace, pool_type=pool)
+    return do.semseg_head(sd, feats, case["num_frames"], trace=trace, pool_type=pool)

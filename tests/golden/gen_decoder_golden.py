@@ -33,17 +33,18 @@ import decoder_cases as dc  # noqa: E402
 def reference_head(case):
     cfg.INPUT.update_param("NUM_FRAMES", case["num_frames"])      # heads read it at construction (common.py:15,28)
     norm = partial(nn.GroupNorm, 32)
+    pool = {"avg": nn.AvgPool3d, "max": nn.MaxPool3d}[case.get("pool", "avg")]       # POOLER_REGISTRY, model_builder.py:28-30
     if case["kind"] == "embedding":
         return EMBEDDING_HEAD_REGISTRY["squeeze_expand_decoder"](
             case["in_channels"], case["inter"], case["embedding_size"], tanh_activation=case["tanh"],
-            seediness_output=case["seediness_output"], experimental_dims=case["dim_mode"], PoolType=nn.AvgPool3d,
+            seediness_output=case["seediness_output"], experimental_dims=case["dim_mode"], PoolType=pool,
             NormType=norm)
     if case["kind"] == "seediness":
         return SEEDINESS_HEAD_REGISTRY["squeeze_expand_decoder"](case["in_channels"], case["inter"],
-                                                                 PoolType=nn.AvgPool3d, NormType=norm)
+                                                                 PoolType=pool, NormType=norm)
     return SEMSEG_HEAD_REGISTRY["squeeze_expand_decoder"](
         case["in_channels"], case["num_out"] - 1, inter_channels=case["inter"], feature_scales=[4, 8, 16, 32],
-        foreground_channel=True, PoolType=nn.AvgPool3d, NormType=norm)
+        foreground_channel=True, PoolType=pool, NormType=norm)
 
 
 def main():

@@ -176,12 +176,45 @@ def test_only_parameters_need_grad(cuda_device):
     assert (before - after).abs().max().item() > 0
 
 
-def test_batched_training_fails_loudly(cuda_device):
+def test_batched_training_equals_per_sample_runs(cuda_device):
+    """Batch 2 under autograd (embedding_decoder.py:101-145 accepts any N): outputs equal the per-sample forwards,
+    feature gradients equal the per-sample ones, parameter gradients are their sum."""
     sd, feats, case = dc.build_case("emb_xyt_t8_batch2")
     head = _build_head(case, cuda_device)
     head.load_state_dict(sd, strict=True)
+    torch.manual_seed(3)
+
+    def run(inputs):
+        for p in head.parameters():
+            p.grad = None
+        xs = [f.clone().to(cuda_device).requires_grad_(True) for f in inputs]
+        out = head(xs)
+        weight = torch.linspace(0.5, 1.5, out[0].numel(), device=cuda_device).reshape(out.shape[1:])
+        (out * weight).sum().backward()
+        return out.detach(), [x.grad.clone() for x in xs], {n: p.grad.clone() for n, p in head.named_parameters()}
+
+    out_b, fg_b, pg_b = run(feats)
+    assert out_b.shape[0] == 2
+    total = None
+    for i in range(2):
+        out_i, fg_i, pg_i = run([f[i:i + 1] for f in feats])
+        assert torch.equal(out_b[i:i + 1], out_i)
+        for a, b in zip(fg_b, fg_i):
+            assert torch.equal(a[i:i + 1], b)
+        total = pg_i if total is None else {n: total[n] + pg_i[n] for n in total}
+    for n in pg_b:
+        scale = max(float(total[n].abs().max()), 1e-12)
+        assert float((pg_b[n] - total[n]).abs().max()) <= 1e-6 * scale, n
+
+
+def test_max_pool_training_fails_loudly(cuda_device):
+    import torch.nn as nn
+    from stemseg_b200 import heads
+    head = heads.SeedinessHead(32, [32] * 4, PoolType=nn.MaxPool3d, NormType=lambda c: nn.GroupNorm(32, c),
+                               num_frames=8).to(cuda_device)
+    x = [torch.randn(1, 32, 8, 96 // s, 96 // s, device=cuda_device, requires_grad=True) for s in (32, 16, 8, 4)]
     with pytest.raises(NotImplementedError):
-        head([f.to(cuda_device).requires_grad_(True) for f in feats])
+        head(x)
 
 
 def test_direct_and_transposed_weight_gradients_agree(cuda_device):

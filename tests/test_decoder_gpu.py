@@ -23,17 +23,18 @@ def build_head(case, sd, device, precision="fp32"):
     import torch.nn as nn
     from stemseg_b200 import heads
     norm = partial(nn.GroupNorm, 32)
+    pool = {"avg": nn.AvgPool3d, "max": nn.MaxPool3d}[case.get("pool", "avg")]
     if case["kind"] == "embedding":
         head = heads.EmbeddingHead(case["in_channels"], case["inter"], case["embedding_size"],
                                    tanh_activation=case["tanh"], seediness_output=case["seediness_output"],
-                                   experimental_dims=case["dim_mode"], PoolType=nn.AvgPool3d, NormType=norm,
+                                   experimental_dims=case["dim_mode"], PoolType=pool, NormType=norm,
                                    num_frames=case["num_frames"], precision=precision)
     elif case["kind"] == "seediness":
-        head = heads.SeedinessHead(case["in_channels"], case["inter"], PoolType=nn.AvgPool3d, NormType=norm,
+        head = heads.SeedinessHead(case["in_channels"], case["inter"], PoolType=pool, NormType=norm,
                                    num_frames=case["num_frames"], precision=precision)
     else:
         head = heads.SemsegHead(case["in_channels"], case["num_out"] - 1, inter_channels=case["inter"],
-                                feature_scales=[4, 8, 16, 32], foreground_channel=True, PoolType=nn.AvgPool3d,
+                                feature_scales=[4, 8, 16, 32], foreground_channel=True, PoolType=pool,
                                 NormType=norm, num_frames=case["num_frames"], precision=precision)
     head.load_state_dict(sd, strict=True)        # identical keys / shapes to the reference heads
     return head.to(device).eval()
@@ -347,7 +348,7 @@ def test_unsupported_options_fail_loudly():
     import torch.nn as nn
     from stemseg_b200 import heads
     with pytest.raises(NotImplementedError):
-        heads.SeedinessHead(32, [32] * 4, PoolType=nn.MaxPool3d, num_frames=8)
+        heads.SeedinessHead(32, [32] * 4, PoolType=nn.AdaptiveAvgPool3d, num_frames=8)
     with pytest.raises(NotImplementedError):
         heads.SeedinessHead(32, [32] * 4, NormType=nn.BatchNorm3d, num_frames=8)
     with pytest.raises(NotImplementedError):
