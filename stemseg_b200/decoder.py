@@ -407,6 +407,9 @@ class HeadSet(object):
         self.fuse_stats = True              # GroupNorm statistics from the conv epilogue (unsplit layers)
         self.chunk_long_layers = True       # long layers as short-lived CTAs + high-priority side branches
         self.pools, self.tscale = pool_schedule(num_frames)
+        self.exact = any(s.weights.exact for s in self.specs)      # e.g. max-pool heads: no single-product fp16 blocks
+        if any(s.weights.exact != self.exact for s in self.specs):
+            raise ValueError("linked heads must agree on exact / fast operand formats")
         # first conv of every block: heads are fused along the GEMM N dimension in GROUPS whose total width keeps the
         # widest N tile (a multiple of 256, or anything up to 256); e.g. embedding (128) + semseg (256) = 384 would fall
         # back to three N=128 tiles, so those two run as separate launches (N=256 and N=128) instead
@@ -447,7 +450,7 @@ class HeadSet(object):
                 full = y.sum(0) if y.dim() == 6 else y.clone()
                 trace[1]["%s.0.conv" % name] = full[..., c0:c0 + conv.cout]
             # operands of the block's later stages use the block's format; its last output feeds a merge (head format)
-            fmt = block_planes(self.planes, name)
+            fmt = block_planes(self.planes, name, self.exact)
             a = group_norm_relu_pool(y, gamma, beta, spec.num_groups, spec.eps,
                                      spec.pool_mode if (self.pools[0] and name != "block_4x") else POOL_NONE,
                                      fmt if n_stages > 1 else self.planes, channel_slice=(c0, conv.cout), stat=stat)
@@ -568,7 +571,7 @@ class HeadSet(object):
 
     def pack_inputs(self, feats_32_16_8_4, out=None):
         """D0: the four feature maps -> operand planes in the format of the scale block that reads them."""
-        return [pack_activation(f, block_planes(self.planes, name), out=None if out is None else out[b])
+        return [pack_activation(f, block_planes(self.planes, name, self.exact), out=None if out is None else out[b])
                 for b, ((name, _), f) in enumerate(zip(BLOCKS, feats_32_16_8_4))]
 
     def _capture(self, feats, dev):

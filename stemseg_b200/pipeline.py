@@ -234,7 +234,10 @@ class SubclipPipeline(object):
             entry = self._step_graphs.get(key)
             if entry is None:
                 entry = self._capture_step(emb_in, fg_mask)
-                entry["stream"] = torch.cuda.Stream(device=dev)
+                # high priority: the operand packing of step i+1 (eager launches on this stream) must not queue behind
+                # the thousands of CTAs of step i's 4x GEMM (normal priority, captured in the graph) -- it is HBM work
+                # that hides under that GEMM, and the step's own GEMM can then start the moment the previous one ends
+                entry["stream"] = torch.cuda.Stream(device=dev, priority=-1)
                 self._step_graphs.put(key, entry)
             caller = torch.cuda.current_stream(dev)
             run_stream = entry["stream"] if self.steps_in_flight > 1 else caller

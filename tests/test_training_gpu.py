@@ -152,6 +152,44 @@ def test_graph_steps_track_the_autograd_steps(cuda_device):
         assert float((p_a - p_g).norm() / p_a.norm()) <= 1e-6
 
 
+def test_split_backward_and_lr_schedule_under_graphs(cuda_device):
+    """(1) The data-parallel schedule (backward cut in two graphs so that the all-reduce of the block_32x / block_16x
+    gradients overlaps the long block_8x / block_4x backward) follows the same trajectory as the single-graph step.
+    (2) set_lr() between steps takes effect in graph mode (the captured SGD launches read the hyper-parameters from
+    device memory): a schedule lr_k = lr0 * 0.5^k matches the autograd trainer driven with the same schedule,
+    and differs from a constant-lr run."""
+    from stemseg_b200.losses import EmbeddingLoss
+    from stemseg_b200.training import DecoderTrainer
+    t, h4, w4 = 4, 24, 32
+    feats = do.seeded_features(703, 1, 32, t, h4, w4)
+    case = lo.seeded_case(seed=704, t=t, h=h4, w=w4, embedding_size=4, n_free=2, instances=2)
+
+    def run(use_graph, split, schedule):
+        emb, seed, _, _ = _small_heads(cuda_device)
+        crit = EmbeddingLoss(4, embedding_size=4, nbr_free_dims=2, free_dim_stds=[0.3, 0.3],
+                             weight_variance_smoothness=10.0, weight_lovasz=1.0, weight_regularization=0.001,
+                             weight_seediness=1.0, weight=1.0)
+        trainer = DecoderTrainer({"embedding": emb, "seediness": seed}, crit, lr=0.05, use_graph=use_graph)
+        trainer.split_backward = split
+        for flat in trainer.flats:
+            assert 0 < flat.prefix_end < flat.numel and flat.prefix_end % 4 == 0
+        targets = [{"masks": case["masks"].to(cuda_device), "ignore_masks": case["ignore"].to(cuda_device)}]
+        for step in range(3):
+            if schedule:
+                trainer.set_lr(0.05 * 0.5 ** step)
+            fdev = [(f * (1.0 + 0.1 * step)).to(cuda_device).requires_grad_(True) for f in feats]
+            trainer.step(fdev, targets)
+        torch.cuda.synchronize()
+        return torch.cat([f.data.clone() for f in trainer.flats]).cpu()
+
+    ref_sched = run(False, False, True)
+    for split in (False, True):
+        got = run(True, split, True)
+        assert float((ref_sched - got).norm() / ref_sched.norm()) <= 1e-6, split
+    const = run(True, True, False)
+    assert float((ref_sched - const).norm() / ref_sched.norm()) > 1e-4
+
+
 def test_semseg_config_trainer_step(cuda_device):
     """YouTube-VIS / KITTI-MOTS wiring: embedding head with its own seediness channel + semseg head with a foreground
     channel.  The CUDA-graph step (three... two heads on two streams) and the autograd step must produce the same
