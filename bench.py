@@ -386,6 +386,50 @@ def time_incumbent_gpu_heads(device, reps=5):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# opt-in variant of the fp32-parity plan: block_8x / block_16x as single fp16 products
+# ------------------------------------------------------------------------------------------------------------------
+def measure_fp16_blocks_variant(device, dev_feats, fg_mask, steps, exact):
+    """Same clip, same weights (seed 42), decoder.set_fast_blocks(("block_8x", "block_16x")): throughput and the
+    per-channel norm-wise deviation from the all-bf16x3 plan's head outputs."""
+    import torch
+    from stemseg_b200 import decoder as D
+    from stemseg_b200.pipeline import build_davis_pipeline
+    D.set_fast_blocks(("block_8x", "block_16x"))
+    try:
+        pipe = build_davis_pipeline(device, num_frames=T, precision="fp32")
+        for _ in range(4):
+            res = pipe(dev_feats, fg_mask=fg_mask)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        queue = []
+        for _ in range(steps):
+            queue.append(pipe.submit(dev_feats, fg_mask=fg_mask))
+            if len(queue) > pipe.steps_in_flight:
+                queue.pop(0).result()
+        for q in queue:
+            q.result()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        worst = 0.0
+        for got, ref in ((res.embeddings, exact.embeddings), (res.variances, exact.variances),
+                         (res.seediness, exact.seediness)):
+            for c in range(ref.shape[0]):
+                worst = max(worst, float((got[c].double() - ref[c].double()).abs().max() / ref[c].abs().max()))
+        del pipe
+    finally:
+        D.set_fast_blocks(())
+        torch.cuda.empty_cache()
+    return {"blocks": ["block_8x", "block_16x"], "ms_per_step": ms, "value": 1e3 / ms, "unit": "clips/s",
+            "worst_channel_deviation_from_default_plan": worst,
+            "tensor_pipe_products_per_mac": round(3 - 2 * (0.162 + 0.122), 3),
+            "note": "opt-in (STEMSEG_FP32_FAST_BLOCKS / decoder.set_fast_blocks): one fp16 product per MAC in block_8x and "
+                    "block_16x; off by default because the per-channel 1e-4 bound is met without margin on some goldens "
+                    "(profiles/r02_fp16_blocks_golden_errors.txt)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # clustering kernel rooflines
 # ------------------------------------------------------------------------------------------------------------------
 def synthetic_points(n, e, device, seed=0):
@@ -980,6 +1024,7 @@ def run_gpu_arm(args, dd):
 
     # rank-0 single-GPU extras (outside every timed region)
     extras = {}
+    exact_result = step_resident() if world == 1 else None
     if world == 1:
         if not args.no_extras:
             for key, fn in (("roofline_cluster_hbm", lambda: cluster_roofline(
@@ -990,6 +1035,8 @@ def run_gpu_arm(args, dd):
                                  device, peaks, T * HP * WP, 4, 2, [0.3, 0.3],
                                  "configs[1] clip at full resolution (--resize_embeddings): 113 MB working set, partly "
                                  "L2-assisted -- the HBM-regime figure is roofline_cluster_hbm")),
+                            ("fp16_blocks_variant", lambda: measure_fp16_blocks_variant(
+                                 device, dev_feats, fg_mask, max(10, args.steps), exact_result)),
                             ("cfg3_bf16", lambda: measure_cfg3(device, max(10, args.steps), max(4, args.warmup), peaks)),
                             ("e2e_frames", lambda: measure_e2e_frames(device, max(5, args.steps // 2), args.warmup)),
                             ("incumbent_gpu", lambda: time_incumbent_gpu_heads(device))):

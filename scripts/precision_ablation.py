@@ -135,7 +135,14 @@ def main():
            "cheapest_admissible_with_2x_margin": {"config": best["config"], "products_per_mac": best["products_per_mac"],
                                                   "worst_channel_error": best["worst_channel_error"]},
            "note": "the dominant kernel (4x layer, 65 % of the MACs) needs 3 products in every admissible mix, so "
-                   "roofline.frac of that launch stays capped at 1/3 of the bf16 peak"}
+                   "roofline.frac of that launch stays capped at 1/3 of the bf16 peak",
+           "gpu_follow_up": "block_8x + block_16x as single fp16 products were then built (STEMSEG_PLANES_FP16) and "
+                            "measured on the B200 over every golden and under the reference's callers with the "
+                            "PER-CHANNEL bound: 1.06e-4 on the 2-frame golden, 9.7e-5 on the free-dimension channels of "
+                            "a random-init model (even block_8x alone), versus <= 1.1e-5 / 2.9e-5 with three products "
+                            "everywhere (profiles/r02_fp16_blocks_golden_errors.txt, r02_fp16_blocks_reference_errors."
+                            "txt).  No mix below 3 products per MAC keeps a margin on every case, so the shipped "
+                            "fp32-parity plan stays at 3.00; the fp16 blocks remain an opt-in (+16 % clips/s)."}
     with open(os.path.join(ROOT, "profiles", "r02_precision_ablation.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("cheapest admissible (2x margin):", best["config"], best["products_per_mac"])

@@ -104,7 +104,7 @@ class _SqueezeExpandTrunk(nn.Module):
         """Kernel-layout weights of this head (repacked when a parameter changes); shared with linked HeadSets.
 
         exact=True (training): every convolution in the head's nominal operand format; the inference plan may run
-        block_8x / block_16x with single fp16 operands in fp32-parity mode (decoder.FP32_FAST_BLOCKS)."""
+        block_8x / block_16x with single fp16 operands in fp32-parity mode when decoder.FP32_FAST_BLOCKS opts in."""
         key = self._cache_key()
         if exact:
             cached = getattr(self, "_packed_exact", None)

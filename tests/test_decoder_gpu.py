@@ -147,6 +147,28 @@ def test_channels_last_producer_is_consumed_without_transpose(cuda_device):
     assert torch.equal(out, out2)
 
 
+def test_fp16_blocks_are_opt_in(cuda_device):
+    """decoder.set_fast_blocks: block_8x / block_16x as single fp16 products.  Off by default (parity mode keeps three
+    products everywhere); when switched on the full-width 8-frame head stays inside 1e-4 but is measurably different."""
+    from stemseg_b200 import decoder as D
+    assert D.FP32_FAST_BLOCKS == ()
+    name = "emb_fullwidth_t8"
+    sd, feats, case = dc.build_case(name)
+    ref = dc.run_oracle(name)
+    dev_feats = [f.to(cuda_device) for f in feats]
+    with torch.no_grad():
+        exact = build_head(case, sd, cuda_device)(dev_feats).cpu()
+    D.set_fast_blocks(("block_8x", "block_16x"))
+    try:
+        with torch.no_grad():
+            fast = build_head(case, sd, cuda_device)(dev_feats).cpu()
+    finally:
+        D.set_fast_blocks(())
+    assert_close(exact, ref, case, 2e-5)
+    assert_close(fast, ref, case, FP32_TOL)
+    assert not torch.equal(fast, exact)
+
+
 def test_deterministic_and_cached_weights(cuda_device):
     name = "seediness_t8"
     sd, feats, case = dc.build_case(name)
