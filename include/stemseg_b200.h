@@ -191,6 +191,9 @@ typedef struct StemsegConvShape {
     int32_t tiles_per_cta;   /* 0: persistent CTAs (one per SM) looping over the tiles; > 0: short-lived CTAs that own
                                 this many consecutive tiles -- lets higher-priority kernels of concurrent branches
                                 obtain SMs while a long layer runs                                                */
+    int32_t out_bf16;        /* 1: `out` receives bf16 [n][t][h][w][cout] instead of fp32 (bf16 mode; split_k == 1 only):
+                                halves the write of the conv output and the read of the GroupNorm-apply pass; the
+                                GroupNorm statistics (stat_partial) are still taken from the fp32 accumulators        */
 } StemsegConvShape;
 
 /* Split that fills the SMs for a latency-bound (few-tile) layer on the current device; 1 for large layers. */
@@ -230,6 +233,10 @@ int32_t stemseg_group_norm_finalize(const float* partial, int64_t partial_sample
  * pool: 0 none, 1 AvgPool3d(3, stride=(2,1,1), padding=1) with divisor 27 (cfg POOL_TYPE "avg"), 2 MaxPool3d with the
  * same window (POOL_TYPE "max", model_builder.py:28-30).  scale_shift NULL = no normalisation (NormType Identity). */
 int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift, int32_t n,
+                               int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool, void* dst_planes,
+                               int32_t planes, void* stream);
+/* Same pass over a bf16 conv output (StemsegConvShape.out_bf16); slices must be 1. */
+int32_t stemseg_norm_relu_pool_bf16in(const void* x, int32_t row_stride, int32_t slices, const float* scale_shift, int32_t n,
                                int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool, void* dst_planes,
                                int32_t planes, void* stream);
 

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libstemseg_b200.so")
 STEMSEG_MAX_EMBEDDING_DIMS = 16
 STEMSEG_MAX_INSTANCES = 64
 STEMSEG_MAX_LOSS_INSTANCES = 32
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 c_void_p, c_size_t, c_int32, c_int64, c_float, c_double = (
     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double)
@@ -30,7 +30,8 @@ class StemsegClusterParams(ctypes.Structure):
 
 class StemsegConvShape(ctypes.Structure):
     _fields_ = [("n", c_int32), ("t", c_int32), ("h", c_int32), ("w", c_int32), ("cin", c_int32), ("cout", c_int32),
-                ("kernel_size", c_int32), ("planes", c_int32), ("split_k", c_int32), ("tiles_per_cta", c_int32)]
+                ("kernel_size", c_int32), ("planes", c_int32), ("split_k", c_int32), ("tiles_per_cta", c_int32),
+                ("out_bf16", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/stemseg_b200.h declares (tests check the two agree)
@@ -130,6 +131,8 @@ PROTOTYPES = {
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stemseg_norm_relu_pool": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "stemseg_norm_relu_pool_bf16in": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                                c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "stemseg_upsample_add": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p, c_int32, c_void_p]),
     "stemseg_head_lowres": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
@@ -153,7 +156,7 @@ KERNELS_PER_CALL = {
     "stemseg_seq_cluster": 1, "stemseg_fg_compact": 3, "stemseg_fg_compact_threshold": 3, "stemseg_fg_gather": 1, "stemseg_fg_compact_mean_threshold": 3, "stemseg_frame_accumulate": 1,
     "stemseg_fg_gather_upsampled": 1,
     "stemseg_pack_activation": 1, "stemseg_pack_conv_weight": 1, "stemseg_conv3d_bf16_planes": 1,
-    "stemseg_group_norm_stats": 2, "stemseg_group_norm_finalize": 1, "stemseg_norm_relu_pool": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
+    "stemseg_group_norm_stats": 2, "stemseg_group_norm_finalize": 1, "stemseg_norm_relu_pool": 1, "stemseg_norm_relu_pool_bf16in": 1, "stemseg_upsample_add": 1, "stemseg_head_output": 1,
     "stemseg_head_lowres": 1, "stemseg_conv1x1_head_output": 1,
     "stemseg_label_pair_histogram": 1, "stemseg_relabel_lut": 1, "stemseg_stitch_subclip": 3,
     "stemseg_rank_map_scatter": 1, "stemseg_mask_writeback": 1,

@@ -20,6 +20,7 @@
 #include "trilinear.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace stemseg {
 namespace {
@@ -55,6 +56,7 @@ struct ConvTcParams {
                                // other graph branches get SMs while it runs
     int num_stages;            // smem pipeline depth
     int operand_fp16;          // 1: the (single) operand planes hold fp16 instead of bf16 values
+    int out_bf16;              // 1: epilogue mode 0 stores bf16 instead of fp32
     float* stat_partial;       // optional [n][cout][tiles_per_sample][2]: per-tile (sum, sum of squares) of every output
                                // channel, consumed by gn_finalize (GroupNorm statistics without re-reading the output)
     int tiles_per_sample;
@@ -431,11 +433,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant
                             const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + q));
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
-                        if (valid) *reinterpret_cast<float4*>(out_row + c + q) = o;
+                        if (valid && !p.out_bf16) *reinterpret_cast<float4*>(out_row + c + q) = o;
                         f[q + 0] = valid ? o.x : 0.f;
                         f[q + 1] = valid ? o.y : 0.f;
                         f[q + 2] = valid ? o.z : 0.f;
                         f[q + 3] = valid ? o.w : 0.f;
+                    }
+                    if (p.out_bf16 && valid) {       // same element index, 2-byte elements: 32 channels = 4 x 16 bytes
+                        __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(p.out) + (out_row - p.out) + c;
+#pragma unroll
+                        for (int q = 0; q < 32; q += 8) {
+                            __nv_bfloat162 h[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q + 2 * k], f[q + 2 * k + 1]);
+                            *reinterpret_cast<uint4*>(o16 + q) = *reinterpret_cast<const uint4*>(h);
+                        }
                     }
                     if (stats) {
                         float f2[32];
@@ -959,6 +971,8 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     p.bias = bias;
     p.num_stages = 0;
     p.operand_fp16 = s->planes == STEMSEG_PLANES_FP16 ? 1 : 0;
+    p.out_bf16 = s->out_bf16 ? 1 : 0;
+    SS_REQUIRE(!p.out_bf16 || (p.k_slices == 1 && head == nullptr), "conv3d: out_bf16 needs an unsplit plain-store launch");
     p.wgrad_mode = 0;
     p.k_splits = 1;
     p.k_chunks_total = 0;
@@ -1229,6 +1243,7 @@ extern "C" int32_t stemseg_conv3d_wgrad(const void* dyT_planes, const void* xT_p
     p.k_splits = k_splits;
     p.wgrad_mode = 1;
     p.operand_fp16 = 0;
+    p.out_bf16 = 0;
     const int hp = h + 2 * pad, pitch = pad ? (w + 2 + 7) / 8 * 8 : w;
     const int shifts = kernel_size == 3 ? 3 : 1;
     for (int tap = 0; tap < 27; ++tap) {

@@ -9,6 +9,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 namespace stemseg {
 namespace {
 
@@ -312,12 +314,28 @@ __global__ void __launch_bounds__(256) gn_relu_pool_kernel(const float* __restri
     }
 }
 
+// 4 consecutive channels of a conv output row: fp32 (16 bytes) or bf16 (8 bytes, StemsegConvShape.out_bf16)
+template <typename XT>
+__device__ __forceinline__ float4 load_quad(const XT* row, int q);
+template <>
+__device__ __forceinline__ float4 load_quad<float>(const float* row, int q) {
+    return __ldg(reinterpret_cast<const float4*>(row) + q);
+}
+template <>
+__device__ __forceinline__ float4 load_quad<__nv_bfloat16>(const __nv_bfloat16* row, int q) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row) + q);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
 // Pooled variant with column reuse: one thread produces kPoolW consecutive outputs along W for one channel quad; the
 // (t,h)-summed columns are shared between neighbouring outputs (54 loads per 4 outputs instead of 108).
 constexpr int kPoolW = 4;
 
-template <bool MAXPOOL>
-__global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
+template <bool MAXPOOL, typename XT>
+__global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const XT* __restrict__ x, const float* __restrict__ scale_shift,
                                                               int n, int t, int h, int w, int c, int t_out, int row_stride,
                                                               __nv_bfloat16* __restrict__ dst, size_t plane_elems,
                                                               int planes) {
@@ -348,12 +366,12 @@ __global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __res
             for (int dh = -1; dh <= 1; ++dh) {
                 const int hi = hh + dh;
                 if (hi < 0 || hi >= h) continue;
-                const float* rowp = x + ((static_cast<size_t>(nn) * t + ti) * h + hi) * static_cast<size_t>(w) * row_stride;
+                const XT* rowp = x + ((static_cast<size_t>(nn) * t + ti) * h + hi) * static_cast<size_t>(w) * row_stride;
 #pragma unroll
                 for (int k = 0; k < kPoolW + 2; ++k) {
                     const int wi = w0 + k - 1;
                     if (wi < 0 || wi >= w) continue;
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(rowp + static_cast<size_t>(wi) * row_stride) + q);
+                    const float4 a = load_quad<XT>(rowp + static_cast<size_t>(wi) * row_stride, q);
                     const float v0 = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f), v1 = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
                     const float v2 = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f), v3 = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
                     if (MAXPOOL) {
@@ -382,7 +400,8 @@ __global__ void __launch_bounds__(256) gn_relu_pool_w4_kernel(const float* __res
 
 // flat variant of gn_relu_pool_kernel<false> for row_stride == c and one slice (the big 4x layer): no index
 // decomposition, two independent 16-byte loads in flight per thread
-__global__ void __launch_bounds__(256) gn_relu_flat_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift,
+template <typename XT>
+__global__ void __launch_bounds__(256) gn_relu_flat_kernel(const XT* __restrict__ x, const float* __restrict__ scale_shift,
                                                            long long quads_per_sample, int quads, int row_quads,
                                                            long long total_quads, __nv_bfloat16* __restrict__ dst,
                                                            size_t plane_elems, int planes) {
@@ -391,9 +410,9 @@ __global__ void __launch_bounds__(256) gn_relu_flat_kernel(const float* __restri
         const long long i1 = i0 + stride;
         const bool has1 = i1 < total_quads;
         // source rows may be wider than the normalised slice (channel slice of a multi-head conv output)
-        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x) + (i0 / quads) * row_quads + (i0 % quads));
+        const float4 a0 = load_quad<XT>(x + (i0 / quads) * row_quads * 4, static_cast<int>(i0 % quads));
         float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has1) a1 = __ldcs(reinterpret_cast<const float4*>(x) + (i1 / quads) * row_quads + (i1 % quads));
+        if (has1) a1 = load_quad<XT>(x + (i1 / quads) * row_quads * 4, static_cast<int>(i1 % quads));
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !has1) break;
@@ -716,7 +735,8 @@ extern "C" int32_t stemseg_group_norm_finalize(const float* partial, int64_t par
     return STEMSEG_OK;
 }
 
-extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift,
+template <typename XT>
+static int32_t norm_relu_pool_impl(const XT* x, int32_t row_stride, int32_t slices, const float* scale_shift,
                                           int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool,
                                           void* dst_planes, int32_t planes, void* stream_) {
     SS_REQUIRE(x && dst_planes, "norm_relu_pool: null pointer");
@@ -734,25 +754,42 @@ extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, in
     const long long total = 1ll * n * t_out * h * w * (c / 4);
     auto* dst = static_cast<__nv_bfloat16*>(dst_planes);
     if (pool == 1 && slices == 1)
-        gn_relu_pool_w4_kernel<false><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
+        gn_relu_pool_w4_kernel<false, XT><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
     else if (pool == 2 && slices == 1)
-        gn_relu_pool_w4_kernel<true><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
+        gn_relu_pool_w4_kernel<true, XT><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
-    else if (pool == 1)
+    else if (slices == 1)
+        gn_relu_flat_kernel<XT><<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
+            x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, row_stride / 4, total, dst, plane_elems, planes);
+    else if constexpr (!std::is_same<XT, float>::value) {
+        set_error("norm_relu_pool: a bf16 conv output must be a single slice");
+        return STEMSEG_ERR_INVALID_ARGUMENT;
+    } else if (pool == 1)
         gn_relu_pool_kernel<1><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     else if (pool == 2)
         gn_relu_pool_kernel<2><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
-    else if (slices == 1)
-        gn_relu_flat_kernel<<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
-            x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, row_stride / 4, total, dst, plane_elems, planes);
     else
         gn_relu_pool_kernel<0><<<grid_for(total, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, slices, slice_stride, dst, plane_elems, planes);
     SS_CUDA_OK(cudaGetLastError());
     return STEMSEG_OK;
+}
+
+extern "C" int32_t stemseg_norm_relu_pool(const float* x, int32_t row_stride, int32_t slices, const float* scale_shift,
+                                          int32_t n, int32_t t, int32_t h, int32_t w, int32_t c, int32_t pool,
+                                          void* dst_planes, int32_t planes, void* stream_) {
+    return norm_relu_pool_impl<float>(x, row_stride, slices, scale_shift, n, t, h, w, c, pool, dst_planes, planes, stream_);
+}
+
+extern "C" int32_t stemseg_norm_relu_pool_bf16in(const void* x, int32_t row_stride, int32_t slices,
+                                                 const float* scale_shift, int32_t n, int32_t t, int32_t h, int32_t w,
+                                                 int32_t c, int32_t pool, void* dst_planes, int32_t planes, void* stream_) {
+    SS_REQUIRE(slices == 1, "norm_relu_pool_bf16in: slices must be 1");
+    return norm_relu_pool_impl<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), row_stride, slices, scale_shift, n, t, h,
+                                              w, c, pool, dst_planes, planes, stream_);
 }
 
 extern "C" int32_t stemseg_upsample_add(const float* z, const float* y_low, int32_t n, int32_t t, int32_t h,

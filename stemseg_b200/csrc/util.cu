@@ -48,5 +48,5 @@ int require_sm100() {
 }  // namespace stemseg
 
 extern "C" const char* stemseg_last_error(void) { return stemseg::g_error; }
-extern "C" int32_t stemseg_abi_version(void) { return 21; }
+extern "C" int32_t stemseg_abi_version(void) { return 22; }
 extern "C" int32_t stemseg_check_device(void) { return stemseg::require_sm100(); }

@@ -155,7 +155,7 @@ CHUNK_MIN_TILES_PER_SM = 4
 CHUNK_TILES = 2
 
 
-def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked=False):
+def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked=False, out_bf16=False):
     """Planes x PackedConv -> fp32 NDHWC tensor [n,t,h,w,cout] (tcgen05 implicit GEMM).
 
     With allow_split the library may split the taps over several CTAs for layers with fewer tiles than SMs; the
@@ -166,7 +166,7 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked
     if act.planes != packed.planes:
         raise ValueError("activation / weight precision mismatch (%s vs %s)" % (act.planes, packed.planes))
     shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, packed.kernel_size, act.planes,
-                                  1, 0)
+                                  1, 0, 0)
     if chunked:
         tiles = lib.stemseg_conv3d_tiles_per_sample(shape) * act.n * max(1, packed.cout // 256)
         if tiles >= CHUNK_MIN_TILES_PER_SM * torch.cuda.get_device_properties(act.tensor.device).multi_processor_count:
@@ -179,8 +179,12 @@ def conv3d(act, packed, max_ctas=0, allow_split=False, want_stats=False, chunked
             out = torch.empty((shape.split_k, act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
                               device=act.tensor.device)
         else:
-            out = torch.empty((act.n, act.t, act.h, act.w, packed.cout), dtype=torch.float32,
-                              device=act.tensor.device)
+            # bf16 mode: the unsplit conv output can be stored as bf16 (the GroupNorm statistics still come from the
+            # fp32 accumulators in the epilogue); split layers keep fp32 partial sums
+            store_bf16 = bool(out_bf16 and want_stats)
+            shape.out_bf16 = 1 if store_bf16 else 0
+            out = torch.empty((act.n, act.t, act.h, act.w, packed.cout),
+                              dtype=torch.bfloat16 if store_bf16 else torch.float32, device=act.tensor.device)
             if want_stats:     # per-tile channel sums straight from the accumulators (GroupNorm statistics)
                 tiles = lib.stemseg_conv3d_tiles_per_sample(shape)
                 stat = torch.empty((act.n, packed.cout, tiles, 2), dtype=torch.float32, device=act.tensor.device)
@@ -214,7 +218,8 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
     n, t, h, w, c_total = y.shape[-5:]
     c0, c = (0, c_total) if channel_slice is None else channel_slice
     dev = y.device
-    x_ptr = _lib.c_void_p(y.data_ptr() + 4 * c0)
+    y_bf16 = y.dtype == torch.bfloat16
+    x_ptr = _lib.c_void_p(y.data_ptr() + (2 if y_bf16 else 4) * c0)
     with torch.cuda.device(dev):
         scale_shift = None
         mean_rstd_out = None
@@ -224,6 +229,8 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
             if c % num_groups != 0:
                 raise ValueError("channels %d not divisible by %d groups" % (c, num_groups))
             scale_shift = torch.empty((n, c, 2), dtype=torch.float32, device=dev)
+            if stat is None and y_bf16:
+                raise ValueError("a bf16 conv output needs the epilogue statistics")
             if stat is not None:          # statistics came out of the conv epilogue: finalize only
                 chunks = stat.shape[2]
                 part_ptr = _lib.c_void_p(stat.data_ptr() + 4 * c0 * chunks * 2)
@@ -243,8 +250,9 @@ def group_norm_relu_pool(y, gamma, beta, num_groups, eps, pool, planes, channel_
             slices = 1                               # the statistics pass summed the split-K slices into slice 0
         t_out = (t - 1) // 2 + 1 if pool else t
         dst = torch.empty((plane_count(planes), n, t_out, h, w, c), dtype=torch.bfloat16, device=dev)
-        _check(lib.stemseg_norm_relu_pool(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c,
-                                          int(pool), _lib.ptr(dst), planes, _lib.stream_ptr()))      # True == POOL_AVG
+        apply = lib.stemseg_norm_relu_pool_bf16in if y_bf16 else lib.stemseg_norm_relu_pool
+        _check(apply(x_ptr, c_total, slices, _lib.ptr(scale_shift), n, t, h, w, c, int(pool), _lib.ptr(dst), planes,
+                     _lib.stream_ptr()))      # pool: True == POOL_AVG
     if saved is not None:
         saved["scale_shift"], saved["mean_rstd"] = scale_shift, mean_rstd_out
     return Planes(dst, n, t_out, h, w, c, planes)
@@ -319,7 +327,7 @@ def fused_merge_head_output(act, packed, y_low, t_scale, spec, max_ctas=0):
     if (act.n, act.t, act.h, act.w) != (n, tl * t_scale, 2 * hl, 2 * wl) or packed.cout != c:
         raise ValueError("fused_merge_head_output: low-res %s does not upsample by (%d,2,2) to %s" % (
             tuple(y_low.shape), t_scale, (act.n, act.t, act.h, act.w, packed.cout)))
-    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, 1, act.planes, 1, 0)
+    shape = _lib.StemsegConvShape(act.n, act.t, act.h, act.w, packed.cin, packed.cout, 1, act.planes, 1, 0, 0)
     with torch.cuda.device(y_low.device):
         p_low = torch.empty((n, tl, hl, wl, spec.n_out), dtype=torch.float32, device=y_low.device)
         _check(lib.stemseg_head_lowres(_lib.ptr(y_low), n * tl * hl * wl, c, _lib.ptr(spec.weight), spec.n_out,
@@ -418,6 +426,7 @@ class HeadSet(object):
         self.fuse_output_heads = True       # conv_4 merge GEMM + output heads in one kernel (epilogue fusion)
         self.fuse_stats = True              # GroupNorm statistics from the conv epilogue (unsplit layers)
         self.chunk_long_layers = True       # long layers as short-lived CTAs + high-priority side branches
+        self.bf16_conv_outputs = planes == 1    # bf16 mode: unsplit conv outputs stored as bf16 (half the HBM bytes)
         self.pools, self.tscale = pool_schedule(num_frames)
         self.exact = any(s.weights.exact for s in self.specs)      # e.g. max-pool heads: no single-product fp16 blocks
         if any(s.weights.exact != self.exact for s in self.specs):
@@ -440,7 +449,8 @@ class HeadSet(object):
         whose long GEMM stays on the normal-priority main stream while everything after it is latency-bound."""
         first = {}                                   # head index -> (conv output, statistics, channel offset)
         for fused, members in self.first_stage[name]:
-            res = conv3d(a_in, fused, allow_split=True, want_stats=self.fuse_stats, chunked=self.chunk_long_layers)
+            res = conv3d(a_in, fused, allow_split=True, want_stats=self.fuse_stats, chunked=self.chunk_long_layers,
+                         out_bf16=self.bf16_conv_outputs)
             y, stat = res if self.fuse_stats else (res, None)
             KEEP.extend((y, stat))
             c0 = 0
@@ -469,7 +479,7 @@ class HeadSet(object):
             KEEP.append(a.tensor)
             for j in range(1, n_stages):
                 conv, gamma, beta = spec.weights.stages[name][j]
-                res = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats)
+                res = conv3d(a, conv, allow_split=True, want_stats=self.fuse_stats, out_bf16=self.bf16_conv_outputs)
                 yj, statj = res if self.fuse_stats else (res, None)
                 KEEP.extend((yj, statj))
                 if trace is not None and hi == trace[0]:
