@@ -58,6 +58,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "timeline":
     for e in evs:
         name = e.name.replace("void ", "").replace("stemseg::(anonymous namespace)::", "").split("(")[0][:60]
         print("%9.1f %8.1f  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, name))
+elif len(sys.argv) > 1 and sys.argv[1] == "fp32":
+    # configs[1]: 8 frames, fp32-parity arithmetic (1.13 TFLOP algorithmic per clip)
+    t16 = 8
+    feats = {s: f.to(device) for s, f in bench.make_features_cpu(seed=0, t=t16).items()}
+    mask = torch.ones((t16, bench.H4, bench.W4), dtype=torch.uint8, device=device)
+    flops = 2 * 2 * 282.43e9
+    for depth in (1, 2, 3):
+        measure(depth, precision="fp32")
 else:
     for depth in (1, 2, 3, 4):
         measure(depth)

@@ -22,9 +22,9 @@ DEFAULT_FRAME_OVERLAP = {"davis": 6, "ytvis": 4, "kittimots": 4}      # defaults
 
 def get_subsequence_frames(seq_len, subseq_len, dataset_name=None, frame_overlap=-1):
     """Overlapping windows of a video (main.py:23-49).  Returns (list of frame-index lists, padded-frame flags|None)."""
+    if dataset_name not in DEFAULT_FRAME_OVERLAP:          # main.py:26-33: unknown datasets raise before anything else
+        raise NotImplementedError()
     if frame_overlap <= 0:
-        if dataset_name not in DEFAULT_FRAME_OVERLAP:
-            raise NotImplementedError()
         frame_overlap = DEFAULT_FRAME_OVERLAP[dataset_name]
     assert frame_overlap < subseq_len
     if seq_len < subseq_len:                           # short video: repeat frame 0 (main.py:37-39)

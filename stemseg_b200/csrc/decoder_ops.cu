@@ -406,33 +406,57 @@ __global__ void __launch_bounds__(256) gn_relu_flat_kernel(const XT* __restrict_
                                                            long long total_quads, __nv_bfloat16* __restrict__ dst,
                                                            size_t plane_elems, int planes) {
     const long long stride = 1ll * gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i0 < total_quads; i0 += 2 * stride) {
-        const long long i1 = i0 + stride;
-        const bool has1 = i1 < total_quads;
-        // source rows may be wider than the normalised slice (channel slice of a multi-head conv output)
-        const float4 a0 = load_quad<XT>(x + (i0 / quads) * row_quads * 4, static_cast<int>(i0 % quads));
-        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has1) a1 = load_quad<XT>(x + (i1 / quads) * row_quads * 4, static_cast<int>(i1 % quads));
+    auto apply = [&](long long i, const float4 a) {
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (scale_shift) {
+            const long long nn = i / quads_per_sample;
+            const int q = static_cast<int>(i % quads);
+            const float4* tab = reinterpret_cast<const float4*>(scale_shift) + (nn * quads + q) * 2;
+            const float4 t0 = __ldg(tab), t1 = __ldg(tab + 1);
+            sc[0] = t0.x; sh[0] = t0.y; sc[1] = t0.z; sh[1] = t0.w;
+            sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
+        }
+        float r[4];
+        r[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
+        r[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
+        r[2] = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
+        r[3] = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
+        store_planes4(dst, plane_elems, planes, static_cast<size_t>(i) * 4, r);
+    };
+    if constexpr (std::is_same<XT, __nv_bfloat16>::value) {
+        // bf16 rows: 8 channels (one 16-byte load) per item, two independent items in flight per thread; the host
+        // guarantees an even number of quads per row
+        const long long total_octs = total_quads / 2;
+        const int octs = quads / 2, row_octs = row_quads / 2;
+        for (long long o0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x; o0 < total_octs; o0 += 2 * stride) {
+            const long long o1 = o0 + stride;
+            const bool has1 = o1 < total_octs;
+            const uint4 r0 = __ldcs(reinterpret_cast<const uint4*>(x) + (o0 / octs) * row_octs + (o0 % octs));
+            uint4 r1 = make_uint4(0u, 0u, 0u, 0u);
+            if (has1) r1 = __ldcs(reinterpret_cast<const uint4*>(x) + (o1 / octs) * row_octs + (o1 % octs));
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !has1) break;
-            const long long i = u == 0 ? i0 : i1;
-            const float4 a = u == 0 ? a0 : a1;
-            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-            if (scale_shift) {
-                const long long nn = i / quads_per_sample;
-                const int q = static_cast<int>(i % quads);
-                const float4* tab = reinterpret_cast<const float4*>(scale_shift) + (nn * quads + q) * 2;
-                const float4 t0 = __ldg(tab), t1 = __ldg(tab + 1);
-                sc[0] = t0.x; sh[0] = t0.y; sc[1] = t0.z; sh[1] = t0.w;
-                sc[2] = t1.x; sh[2] = t1.y; sc[3] = t1.z; sh[3] = t1.w;
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !has1) break;
+                const uint4 raw = u == 0 ? r0 : r1;
+                const long long o = u == 0 ? o0 : o1;
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
+                const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
+                apply(2 * o, make_float4(f0.x, f0.y, f1.x, f1.y));
+                apply(2 * o + 1, make_float4(f2.x, f2.y, f3.x, f3.y));
             }
-            float r[4];
-            r[0] = fmaxf(fmaf(a.x, sc[0], sh[0]), 0.f);
-            r[1] = fmaxf(fmaf(a.y, sc[1], sh[1]), 0.f);
-            r[2] = fmaxf(fmaf(a.z, sc[2], sh[2]), 0.f);
-            r[3] = fmaxf(fmaf(a.w, sc[3], sh[3]), 0.f);
-            store_planes4(dst, plane_elems, planes, static_cast<size_t>(i) * 4, r);
+        }
+    } else {
+        for (long long i0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i0 < total_quads; i0 += 2 * stride) {
+            const long long i1 = i0 + stride;
+            const bool has1 = i1 < total_quads;
+            // source rows may be wider than the normalised slice (channel slice of a multi-head conv output)
+            const float4 a0 = __ldcs(reinterpret_cast<const float4*>(x) + (i0 / quads) * row_quads + (i0 % quads));
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has1) a1 = __ldcs(reinterpret_cast<const float4*>(x) + (i1 / quads) * row_quads + (i1 % quads));
+            apply(i0, a0);
+            if (has1) apply(i1, a1);
         }
     }
 }
@@ -759,9 +783,15 @@ static int32_t norm_relu_pool_impl(const XT* x, int32_t row_stride, int32_t slic
     else if (pool == 2 && slices == 1)
         gn_relu_pool_w4_kernel<true, XT><<<grid_for((total + kPoolW - 1) / kPoolW, 256, 16), 256, 0, stream>>>(
             x, scale_shift, n, t, h, w, c, t_out, row_stride, dst, plane_elems, planes);
-    else if (slices == 1)
-        gn_relu_flat_kernel<XT><<<grid_for((total + 1) / 2, 256, 8), 256, 0, stream>>>(
+    else if (slices == 1) {
+        if (!std::is_same<XT, float>::value && (c % 8 != 0 || row_stride % 8 != 0)) {
+            set_error("norm_relu_pool: bf16 rows need channel counts that are multiples of 8");
+            return STEMSEG_ERR_INVALID_ARGUMENT;
+        }
+        const long long items = std::is_same<XT, float>::value ? total : total / 2;
+        gn_relu_flat_kernel<XT><<<grid_for((items + 1) / 2, 256, 8), 256, 0, stream>>>(
             x, scale_shift, 1ll * t * h * w * (c / 4), c / 4, row_stride / 4, total, dst, plane_elems, planes);
+    }
     else if constexpr (!std::is_same<XT, float>::value) {
         set_error("norm_relu_pool: a bf16 conv output must be a single slice");
         return STEMSEG_ERR_INVALID_ARGUMENT;
