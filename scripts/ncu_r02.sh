@@ -1,0 +1,15 @@
+#!/bin/bash
+# ncu evidence for round 2 (one GPU; numbers printed under ncu are never bench values).
+# Outputs under gpurun_out/: r02_launches_bench.csv (every launch of 2 default steps with its device time),
+# r02_conv_fp32.ncu-rep / r02_conv_bf16.ncu-rep (--set full of the tcgen05 conv launches), r02_cluster_e8.ncu-rep
+# (--set full of the streaming clustering kernel on the HBM-resident shape).
+set -x
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r02_launches_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 44 -c 22 -o gpurun_out/r02_conv_fp32 \
+    python scripts/ncu_one_step.py fp32 > gpurun_out/r02_conv_fp32.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 44 -c 22 -o gpurun_out/r02_conv_bf16 \
+    python scripts/ncu_one_step.py bf16 > gpurun_out/r02_conv_bf16.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:seq_cluster -s 1 -c 1 -o gpurun_out/r02_cluster_e8 \
+    python scripts/profile_cluster.py > gpurun_out/r02_cluster_e8.log 2>&1
+ls -la gpurun_out | grep r02
