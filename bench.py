@@ -962,6 +962,8 @@ def run_gpu_arm(args, dd):
         pipe.cluster(emb, var, seedi, fg_mask)             # lazy kernel loading of the eager gather / cluster path
         stages["heads_ms"], (emb, var, seedi, _) = ev_time(lambda: pipe.run_heads(dev_feats))
         stages["gather_cluster_ms"], _ = ev_time(lambda: pipe.cluster(emb, var, seedi, fg_mask))
+        # what a caller that processes ONE clip at a time sees: the whole step as one graph replay, synchronous
+        stages["single_clip_latency_ms"], _ = ev_time(step_resident)
 
     # per-launch durations of the tcgen05 conv kernel: the same plan launched eagerly (the timed region replays it
     # as a CUDA graph, where individual launches cannot be bracketed), CUDA events on the launching stream

@@ -53,7 +53,7 @@ def training_forward(head, feats, in_planes=None):
     pools, tscale = D.pool_schedule(head.num_frames)
     has_norm = head._has_norm
     saved = {"blocks": {}, "merges": [], "planes": planes, "tscale": tscale}
-    D.KEEP = []
+    D.KEEP.reset()
     branch = []
     for b, (name, n_stages) in enumerate(D.BLOCKS):
         if in_planes is not None:
@@ -95,7 +95,7 @@ def training_forward(head, feats, in_planes=None):
             saved["x4"] = z
             out = D.head_output_x(z, out_spec)
     saved["out_spec"] = out_spec
-    D.KEEP = []
+    D.KEEP.reset()
     if DEBUG_SAVED is not None:
         DEBUG_SAVED.append(saved)
     return out, saved

@@ -402,8 +402,30 @@ def first_stage_groups(couts):
 
 
 # intermediates of the plan currently being built / captured: kept alive so that no buffer is recycled while a
-# parallel branch of the CUDA graph may still read it
-KEEP = []
+# parallel branch of the CUDA graph may still read it.  Thread-local: two pipelines may build / capture plans from
+# different host threads.
+import threading as _threading
+
+
+class _KeepAlive(_threading.local):
+    def __init__(self):
+        self.items = []
+
+    def append(self, x):
+        self.items.append(x)
+
+    def extend(self, xs):
+        self.items.extend(xs)
+
+    def reset(self):
+        self.items = []
+
+    def take(self):
+        items, self.items = self.items, []
+        return items
+
+
+KEEP = _KeepAlive()
 
 
 class HeadSet(object):
@@ -573,13 +595,12 @@ class HeadSet(object):
                 raise ValueError("feature map %s does not have T=NUM_FRAMES=%d" % (tuple(f.shape), self.num_frames))
         dev = feats_32_16_8_4[0].device
         key = tuple((tuple(f.shape), str(f.device)) for f in feats_32_16_8_4)
-        global KEEP
         if trace is not None or not self.use_graph:
-            KEEP = []
+            KEEP.reset()
             with torch.cuda.device(dev):
                 in_planes = self.pack_inputs(feats_32_16_8_4)
                 outs = self._plan(in_planes, trace=trace)
-            KEEP = []
+            KEEP.reset()
             return outs
         entry = self._entries.get(key)
         with torch.cuda.device(dev):
@@ -597,28 +618,27 @@ class HeadSet(object):
                 for b, ((name, _), f) in enumerate(zip(BLOCKS, feats_32_16_8_4))]
 
     def _capture(self, feats, dev):
-        global KEEP
         in_planes = self.pack_inputs(feats)
         # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute, ...) before capturing
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            KEEP = []
+            KEEP.reset()
             self._plan(in_planes)
-            KEEP = []
+            KEEP.reset()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         # high priority: the three small scale branches + the tail after the 4x GEMM (see _plan)
         streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(4)]
-        KEEP = []
+        KEEP.reset()
         before = _lib.KERNEL_LAUNCHES[0]
         with _lib.capture_guard(), torch.cuda.graph(graph):
             outputs = self._plan(in_planes, streams=streams)
             if self._tail_stream is not None:        # join the capture's origin stream
                 torch.cuda.current_stream().wait_event(self._tail_stream.record_event())
         kernels = _lib.KERNEL_LAUNCHES[0] - before
-        keep, KEEP = KEEP, []
+        keep = KEEP.take()
         return {"graph": graph, "in_planes": in_planes, "outputs": outputs, "keep": keep, "kernels": kernels,
                 "streams": streams}
 

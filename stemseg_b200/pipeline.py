@@ -191,20 +191,20 @@ class SubclipPipeline(object):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            D.KEEP = []
+            D.KEEP.reset()
             body(None)
-            D.KEEP = []
+            D.KEEP.reset()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(4)]     # small branches + tail: high priority
         from stemseg_b200 import _lib
-        D.KEEP = []
+        D.KEEP.reset()
         before = _lib.KERNEL_LAUNCHES[0]
         with _lib.capture_guard(), torch.cuda.graph(graph):
             state = body(streams)
         kernels = _lib.KERNEL_LAUNCHES[0] - before
-        keep, D.KEEP = D.KEEP, []
+        keep = D.KEEP.take()
         return {"graph": graph, "in_planes": in_planes, "mask": mask_static, "state": state, "keep": keep,
                 "kernels": kernels, "streams": streams, "planes": group.planes}
 

@@ -42,19 +42,20 @@ def test_cuda_matches_reference_golden(name, golden, cuda_device):
     assert [int(m.sum()) for m in meta['instance_masks']] == golden[name + "/mask_counts"].tolist()
 
 
-@pytest.mark.parametrize("e,nf,n", [(4, 2, 207360), (3, 0, 207360), (8, 0, 414720), (5, 2, 100003), (4, 2, 3317760)])
+@pytest.mark.parametrize("e,nf,n", [(4, 2, 207360), (3, 0, 207360), (8, 0, 414720), (5, 2, 100003), (4, 2, 3317760),
+                                    (8, 0, 6635520)])
 def test_cuda_matches_oracle_large(e, nf, n, cuda_device):
-    """BASELINE config sizes: quarter-res 8x480x864 (207 360 points), cfg3 E=8 (414 720), full-res 3.3 M."""
+    """BASELINE config sizes: quarter-res 8x480x864 (207 360 points), cfg3 E=8 (414 720), full-res 3.3 M, and the
+    HBM-resident cfg3 full-resolution shape (E=8, 8 learned variances, N = 16x480x864 = 6 635 520: bit-mask streaming
+    kernel)."""
     emb, bw, seed = make_points(seed=77 + e, n=n, e=e, n_free=nf, n_blobs=14, noise_frac=0.2)
     clu = dict(primary_prob_thresh=0.5, secondary_prob_thresh=0.3, min_seediness_prob=0.0, n_free_dims=nf,
                free_dim_stds=[0.3, 0.3][:nf], max_instances=20, cluster_label_start=3)
     o_labels, o_meta = co.sequential_cluster(emb, bw, seed, **clu)
     labels, meta = run_cuda(emb, bw, seed, clu, cuda_device, return_label_masks=False)
     got = labels.cpu().numpy()
-    if o_meta['margin_ulps'] >= 1:
-        np.testing.assert_array_equal(got, o_labels)
-    else:   # a point sits exactly on a threshold: still identical (both test d <= d*), recorded for information
-        np.testing.assert_array_equal(got, o_labels)
+    # identical even when a point sits exactly on a threshold (margin_ulps == 0): both sides test d <= d*
+    np.testing.assert_array_equal(got, o_labels)
     assert meta['instance_labels'] == o_meta['instance_labels']
     np.testing.assert_array_equal(np.array(meta['instance_centers'], np.float32),
                                   np.array(o_meta['instance_centers'], np.float32))

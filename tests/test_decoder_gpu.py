@@ -106,7 +106,7 @@ def test_bf16_mode(cuda_device):
     with torch.no_grad():
         out = head([f.to(cuda_device) for f in feats])
     ref = dc.run_oracle(name)
-    assert_close(out.cpu(), ref, case, 2e-2)
+    assert_close(out.cpu(), ref, case, BF16_TOL)
 
 
 def test_permuted_input_views(cuda_device):
@@ -208,6 +208,28 @@ def test_full_size_480p_vs_oracle(t, h4, w4, cuda_device):
     with torch.no_grad():
         out = head([f.to(cuda_device) for f in feats])
     assert_close(out.cpu(), ref, case, FP32_TOL)
+
+
+BF16_TOL = 2e-2
+
+
+def test_cfg3_bf16_full_size_16x480x864(cuda_device):
+    """BASELINE config 3 at size: 16x480x864 clip, real channel widths, bf16 decoder (one tensor-core product per MAC,
+    bf16 conv outputs) against the fp32-parity plan on the same device (itself gated at 1e-4 against the oracle at
+    8x480x864 and on the 16-frame golden).  bf16 operands cannot meet 1e-4 by construction (2^-9 operand
+    rounding); the stated bound for this mode is 2e-2 norm-wise per output channel."""
+    case = dict(kind="embedding", in_channels=256, inter=[256, 256, 128, 128], num_frames=16, n=1, h4=120, w4=216,
+                embedding_size=4, dim_mode="xyff", tanh=True, seediness_output=True)
+    shapes = do.head_parameter_shapes("embedding", 256, case["inter"], embedding_size=4, dim_mode="xyff",
+                                      seediness_output=True)
+    sd = do.seeded_state_dict(shapes, 5252)
+    feats = [f.to(cuda_device) for f in do.seeded_features(5253, 1, 256, 16, 120, 216)]
+    with torch.no_grad():
+        ref = build_head(case, sd, cuda_device, precision="fp32")(feats).cpu()
+        out = build_head(case, sd, cuda_device, precision="bf16")(feats).cpu()
+    assert out.shape == ref.shape == (1, 7, 16, 120, 216)
+    assert_close(out, ref, case, BF16_TOL)
+    assert not torch.equal(out, ref)
 
 
 def test_fused_head_group_matches_separate_heads(cuda_device):
