@@ -416,7 +416,7 @@ class DeviceStitcher(object):
         self.num_frames, self.frame_capacity, self.max_instances = int(num_frames), int(frame_capacity), int(max_instances)
         if max_labels is None:
             max_labels = self.max_instances * (max_subclips if max_subclips is not None else max(1, self.num_frames))
-        self.max_labels = int(max_labels)
+        self.max_labels = min(int(max_labels), 4095)        # csrc/stitch.cu kAssignMaxLabels (shared-memory table)
         with torch.cuda.device(self.device):
             self.frame_labels = torch.empty((self.num_frames, self.frame_capacity), dtype=torch.int64, device=self.device)
             self.frame_count = torch.full((self.num_frames,), -1, dtype=torch.int32, device=self.device)

@@ -241,8 +241,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
 constexpr int kMaxStages = 8;
 constexpr int kHeadJChunkTc = 8;
 
-template <int BLOCK_N, int BLOCK_K, int PLANES>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// MINB = 2: two CTAs per SM (register cap 168, half the shared-memory ring, 2 x 256 TMEM columns) -- used for the fused
+// merge + output-heads launches, whose time is spent in the epilogue warps (J x BLOCK_N FMAs per voxel, tensor pipe
+// 4-8 % active, profiles/r02_conv_ncu_summary.json): twice the epilogue warps per SM
+template <int BLOCK_N, int BLOCK_K, int PLANES, int MINB = 1>
+__global__ void __launch_bounds__(kNumThreads, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap a_map0, const __grid_constant__ CUtensorMap a_map1,
                const __grid_constant__ CUtensorMap b_map0, const __grid_constant__ CUtensorMap b_map1,
                const ConvTcParams p) {
@@ -855,6 +858,22 @@ int launch_variant(const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaS
                   p.head_j);
         return STEMSEG_ERR_UNSUPPORTED;
     }
+    if constexpr (BLOCK_N <= 128) {
+        // fused output heads: epilogue-bound -> two CTAs per SM when two pipeline stages fit in half the shared memory
+        constexpr int kHalfSmem = 110 * 1024;
+        const int stages2 = (kHalfSmem - fixed) / stage;
+        if (p.epi_mode == 1 && stages2 >= 2 && p.tiles_per_cta == 0) {
+            p.num_stages = stages2 > kMaxStages ? kMaxStages : stages2;
+            auto kernel2 = conv_tc_kernel<BLOCK_N, BLOCK_K, PLANES, 2>;
+            SS_CUDA_OK(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHalfSmem));
+            int grid2 = 2 * device_sm_count();
+            if (max_ctas > 0 && grid2 > max_ctas) grid2 = max_ctas;
+            if (grid2 > p.num_tiles) grid2 = p.num_tiles;
+            kernel2<<<grid2, kNumThreads, p.num_stages * stage + fixed, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+            SS_CUDA_OK(cudaGetLastError());
+            return STEMSEG_OK;
+        }
+    }
     p.num_stages = stages;
     const int smem_bytes = stages * stage + fixed;
     auto kernel = conv_tc_kernel<BLOCK_N, BLOCK_K, PLANES>;
@@ -997,6 +1016,8 @@ static int32_t conv3d_impl(const void* act_planes, const void* weight_planes, co
     // BLOCK_K: 64 channels (SWIZZLE_128B) when the stage still leaves >= 3 pipeline stages, else 32 (SWIZZLE_64B)
     int block_k = (s->cin % 64 == 0) ? 64 : 32;
     if (block_k == 64 && plane_count == 2 && block_n == 256) block_k = 32;
+    // fused heads (two CTAs per SM, launch_variant): two-plane stages of 64 channels would not fit twice
+    if (block_k == 64 && plane_count == 2 && head != nullptr && block_n <= 128) block_k = 32;
 
     const size_t act_plane_bytes = static_cast<size_t>(p.n) * p.t * p.h * p.w * p.cin * 2;
     const int64_t k_total = static_cast<int64_t>(p.ntaps) * p.cin;

@@ -190,102 +190,141 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_hist_kernel(const Stitc
     if (err) atomicOr(&a.state[2], err);
 }
 
-__global__ void stitch_assign_kernel(const StitchArgs a, const StitchFrames f) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+constexpr int kAssignThreads = 128;
+constexpr int kAssignMaxLabels = 4095;          // s_size_a lives in shared memory
+
+struct AssignSmem {
+    double cost[kAssocMaxSide * kAssocMaxSide];
+    LsapScratch lsap;
+    long long size_a[kAssignMaxLabels + 1];
+    long long size_b[kAssocMaxSide + 2];
+    long long u1[kAssocMaxSide + 1], u2[kAssocMaxSide + 1];
+    int c1, c2, err, highest;
+};
+
+// One block.  The sequential parts (set ordering, assignment) run in thread 0 on shared memory; everything that only
+// moves or reduces table entries (row / column sums of the joint histogram, the cost matrix, the per-frame statistics)
+// is spread over the block -- a single thread walking thousands of cold global loads made this kernel the serial
+// section of the multi-GPU stitch (0.5 ms per sub-clip; profiles/r02_bench_n8_before_stitch_fix.json).
+__global__ void __launch_bounds__(kAssignThreads) stitch_assign_kernel(const StitchArgs a, const StitchFrames f) {
+    extern __shared__ __align__(16) unsigned char assign_smem_raw[];
+    AssignSmem& sm = *reinterpret_cast<AssignSmem*>(assign_smem_raw);
+    const int tid = threadIdx.x;
     const int k = *a.k_dev;
     const int nb = a.max_instances + 2;
     const long long offset = a.state[0] - 1;
-    int err = 0;
-    if (k > a.max_instances || offset + k > a.max_labels) err |= kErrTooManyLabels;
-    for (int l = 1; l <= a.max_instances + 1; ++l) {
+    const int highest0 = a.state[1];
+    if (tid == 0) {
+        sm.err = 0;
+        sm.c1 = sm.c2 = 0;
+        sm.highest = highest0;
+        if (k > a.max_instances || offset + k > a.max_labels) sm.err |= kErrTooManyLabels;
+    }
+    for (int l = 1 + tid; l <= a.max_instances + 1; l += kAssignThreads) {
         a.lut_local[l - 1] = offset + l;
         a.lut_assoc[l - 1] = offset + l;
     }
-    for (int c = 0; c < a.max_instances; ++c) a.meta_labels[c] = c < k ? offset + c + 1 : -1;
-    for (int j = 0; j < f.n_frames; ++j) {
+    for (int c = tid; c < a.max_instances; c += kAssignThreads) a.meta_labels[c] = c < k ? offset + c + 1 : -1;
+    __syncthreads();
+    for (int j = tid; j < f.n_frames; j += kAssignThreads) {
         const int t = f.frame[j];
         if (!a.is_first && f.overlap[j]) {
-            if (a.frame_count[t] != a.frame_counts[j]) err |= kErrOverlapSize;
+            if (a.frame_count[t] != a.frame_counts[j]) atomicOr(&sm.err, kErrOverlapSize);
         } else if (a.frame_count[t] >= 0) {
-            err |= kErrFrameExists;
+            atomicOr(&sm.err, kErrFrameExists);
         }
     }
-    if (!a.is_first && !(err & kErrTooManyLabels)) {
-        long long vals1[kAssocMaxSide + 1], vals2[kAssocMaxSide + 1], u1[kAssocMaxSide + 1], u2[kAssocMaxSide + 1];
-        long long size_b[kAssocMaxSide + 2];
-        int n1 = 0, n2 = 0;
-        const int highest = a.state[1];
-        // existing labels present in the overlap frames (ascending, like Tensor.unique()), outliers first
-        for (int g = 0; g <= highest && g <= a.max_labels; ++g) {
-            long long s = 0;
-            for (int l = 0; l <= k; ++l) s += a.joint[g * nb + l];
-            if (s > 0) {
+    const bool associate = !a.is_first && k <= a.max_instances && offset + k <= a.max_labels;
+    if (associate) {
+        // row / column sums of the joint histogram (existing id x current local label) over the overlap frames
+        for (int g = tid; g <= highest0 && g <= a.max_labels; g += kAssignThreads) {
+            long long sum = 0;
+            for (int l = 0; l <= k; ++l) sum += a.joint[g * nb + l];
+            sm.size_a[g] = sum;
+        }
+        for (int l = tid; l <= k && l < kAssocMaxSide + 2; l += kAssignThreads) {
+            long long sum = 0;
+            for (int g = 0; g <= highest0 && g <= a.max_labels; ++g) sum += a.joint[g * nb + l];
+            sm.size_b[l] = sum;
+        }
+    }
+    __syncthreads();
+    if (associate && tid == 0) {
+        long long vals1[kAssocMaxSide + 1], vals2[kAssocMaxSide + 1];
+        int n1 = 0, n2 = 0, err = 0;
+        // labels present in the overlap frames, ascending like Tensor.unique(), outliers (-1) first
+        for (int g = 0; g <= highest0 && g <= a.max_labels; ++g)
+            if (sm.size_a[g] > 0) {
                 if (n1 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
                 vals1[n1++] = g == 0 ? -1 : g;
             }
-        }
-        for (int l = 0; l <= k && l < kAssocMaxSide + 2; ++l) {
-            long long s = 0;
-            for (int g = 0; g <= highest && g <= a.max_labels; ++g) s += a.joint[g * nb + l];
-            size_b[l] = s;
-            if (s > 0) {
+        for (int l = 0; l <= k && l < kAssocMaxSide + 2; ++l)
+            if (sm.size_b[l] > 0) {
                 if (n2 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
                 vals2[n2++] = l == 0 ? -1 : offset + l;
             }
-        }
         if (!err) {
-            const int c1 = pyset_order(vals1, n1, u1);
-            const int c2 = pyset_order(vals2, n2, u2);
+            const int c1 = pyset_order(vals1, n1, sm.u1);
+            const int c2 = pyset_order(vals2, n2, sm.u2);
             if (c1 < 0 || c2 < 0) err |= kErrTooManyLabels;
             else {
                 // every current label is > every existing one (offset = next_track_label - 1 >= highest existing label)
                 for (int i = 0; i < c1; ++i)
-                    if (u1[i] > offset) err |= kErrLabelsOverlap;
-                for (int i1 = 0; i1 < c1; ++i1) {
-                    long long size1 = 0;
-                    for (int l = 0; l <= k; ++l) size1 += a.joint[u1[i1] * nb + l];
-                    for (int i2 = 0; i2 < c2; ++i2) {
-                        const int l = static_cast<int>(u2[i2] - offset);
-                        const long long inter = a.joint[u1[i1] * nb + l];
-                        const long long uni = size1 + size_b[l] - inter;
-                        const float iou = __fdiv_rn(static_cast<float>(inter), static_cast<float>(uni));   // fp32 tensors
-                        const float c32 = static_cast<float>(1.0 - static_cast<double>(iou));            // 1. - iou.item()
-                        a.cost[i1 * c2 + i2] = static_cast<double>(c32);
-                    }
-                }
-                int rows[kAssocMaxSide], cols[kAssocMaxSide];
-                const int pairs = lsap_solve(a.cost, c1, c2, rows, cols, *a.lsap);
-                if (pairs < 0) err |= kErrAssignment;
-                for (int q = 0; q < pairs; ++q) {
-                    const long long associated = u1[rows[q]], current = u2[cols[q]];
-                    a.lut_assoc[current - offset - 1] = associated;
-                    for (int c = 0; c < k; ++c)                   // meta_info['instance_labels'].index(current)
-                        if (a.meta_labels[c] == current) { a.meta_labels[c] = associated; break; }
-                }
+                    if (sm.u1[i] > offset) err |= kErrLabelsOverlap;
+                sm.c1 = c1;
+                sm.c2 = c2;
             }
         }
+        if (err) { sm.err |= err; sm.c1 = sm.c2 = 0; }
     }
-    // TrackContainer bookkeeping for the frames added by this sub-clip
-    int highest = a.state[1];
-    for (int j = 0; j < f.n_frames; ++j) {
-        if (!a.is_first && f.overlap[j]) continue;
-        const int t = f.frame[j];
-        a.frame_count[t] = a.frame_counts[j];
-        for (int lbin = 0; lbin <= k && lbin <= a.max_instances; ++lbin) {
-            const int c = a.per_frame[lbin * f.n_frames + j];
-            if (c == 0) continue;
-            const long long label = lbin == 0 ? -1 : a.lut_assoc[lbin - 1];
-            if (label > a.max_labels) { err |= kErrTooManyLabels; continue; }
-            a.track_counts[label + 1] += c;
-            if (t < a.span_lo[label + 1]) a.span_lo[label + 1] = t;
-            if (t > a.span_hi[label + 1]) a.span_hi[label + 1] = t;
-            if (label > highest) highest = static_cast<int>(label);
+    __syncthreads();
+    const int c1 = sm.c1, c2 = sm.c2;
+    for (int idx = tid; idx < c1 * c2; idx += kAssignThreads) {
+        const int i1 = idx / c2, i2 = idx % c2;
+        const int l = static_cast<int>(sm.u2[i2] - offset);
+        const long long inter = a.joint[sm.u1[i1] * nb + l];
+        const long long uni = sm.size_a[sm.u1[i1]] + sm.size_b[l] - inter;
+        const float iou = __fdiv_rn(static_cast<float>(inter), static_cast<float>(uni));   // fp32 tensors in the reference
+        const float c32 = static_cast<float>(1.0 - static_cast<double>(iou));            // 1. - iou.item() into float32
+        sm.cost[idx] = static_cast<double>(c32);
+    }
+    __syncthreads();
+    if (tid == 0 && c1 > 0 && c2 > 0) {
+        int rows[kAssocMaxSide], cols[kAssocMaxSide];
+        const int pairs = lsap_solve(sm.cost, c1, c2, rows, cols, sm.lsap);
+        if (pairs < 0) sm.err |= kErrAssignment;
+        for (int q = 0; q < pairs; ++q) {
+            const long long associated = sm.u1[rows[q]], current = sm.u2[cols[q]];
+            a.lut_assoc[current - offset - 1] = associated;
+            for (int c = 0; c < k; ++c)                   // meta_info['instance_labels'].index(current)
+                if (a.meta_labels[c] == current) { a.meta_labels[c] = associated; break; }
         }
     }
-    a.state[1] = highest;
-    a.state[0] = highest + 1;
-    a.state[3] += 1;
-    if (err) atomicOr(&a.state[2], err);
+    __syncthreads();
+    // TrackContainer bookkeeping for the frames added by this sub-clip (one thread per (frame, label bin))
+    const int bins = (k < a.max_instances ? k : a.max_instances) + 1;
+    for (int idx = tid; idx < f.n_frames * bins; idx += kAssignThreads) {
+        const int j = idx / bins, lbin = idx % bins;
+        if (!a.is_first && f.overlap[j]) continue;
+        const int t = f.frame[j];
+        const int c = a.per_frame[lbin * f.n_frames + j];
+        if (c == 0) continue;
+        const long long label = lbin == 0 ? -1 : a.lut_assoc[lbin - 1];
+        if (label > a.max_labels) { atomicOr(&sm.err, kErrTooManyLabels); continue; }
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.track_counts + label + 1), static_cast<unsigned long long>(c));
+        atomicMin(a.span_lo + label + 1, t);
+        atomicMax(a.span_hi + label + 1, t);
+        atomicMax(&sm.highest, static_cast<int>(label));
+    }
+    for (int j = tid; j < f.n_frames; j += kAssignThreads)
+        if (a.is_first || !f.overlap[j]) a.frame_count[f.frame[j]] = a.frame_counts[j];
+    __syncthreads();
+    if (tid == 0) {
+        a.state[1] = sm.highest;
+        a.state[0] = sm.highest + 1;
+        a.state[3] += 1;
+        if (sm.err) atomicOr(&a.state[2], sm.err);
+    }
 }
 
 __global__ void __launch_bounds__(kStitchThreads) stitch_relabel_kernel(const StitchArgs a, const StitchFrames f) {
@@ -343,6 +382,7 @@ extern "C" int32_t stemseg_stitch_subclip(int64_t* labels, int64_t capacity, con
                max_instances);
     SS_REQUIRE(max_labels >= max_instances && capacity >= 0 && frame_capacity >= 1 && num_frames >= 1,
                "stitch_subclip: bad sizes");
+    SS_REQUIRE(max_labels <= kAssignMaxLabels, "stitch_subclip: max_labels %d > %d", max_labels, kAssignMaxLabels);
     size_t off[6];
     const size_t need = stitch_ws_layout(max_instances, n_frames, max_labels, off);
     SS_REQUIRE(ws_bytes >= need, "stitch_subclip: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -384,7 +424,9 @@ extern "C" int32_t stemseg_stitch_subclip(int64_t* labels, int64_t capacity, con
     if (blocks < 1) blocks = 1;
     stitch_hist_kernel<<<static_cast<unsigned>(blocks), kStitchThreads, 0, stream>>>(a, f);
     SS_CUDA_OK(cudaGetLastError());
-    stitch_assign_kernel<<<1, 32, 0, stream>>>(a, f);
+    SS_CUDA_OK(cudaFuncSetAttribute(stitch_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sizeof(AssignSmem))));
+    stitch_assign_kernel<<<1, kAssignThreads, sizeof(AssignSmem), stream>>>(a, f);
     SS_CUDA_OK(cudaGetLastError());
     stitch_relabel_kernel<<<static_cast<unsigned>(blocks), kStitchThreads, 0, stream>>>(a, f);
     SS_CUDA_OK(cudaGetLastError());
