@@ -55,7 +55,8 @@ def base_config(precision="fp32"):
     return {"workload": WORKLOAD, "clip": [T, H, W], "padded": [T, HP, WP], "grid_points": GRID_POINTS,
             "heads": "davis_1.yaml: embedding (xyff, E=4, V=2) + seediness, inter_channels %s" % (list(INTER),),
             "clustering": "primary 0.5 / secondary 0.3 / min_seediness 0.0 / max_instances 20, all voxels foreground",
-            "precision": precision}
+            "precision": precision,
+            "l2": "inputs larger than L2 (282 MB fp32 pyramid per step vs 126 MB L2)"}
 
 
 def make_features_cpu(seed=0, t=T):
@@ -188,8 +189,8 @@ def run_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     value = steps / dt
     cfg = base_config("fp32")
-    cfg["timing"] = "host wall clock"
     line = {
+        "config_detail": {"timing": "host wall clock", "arithmetic": "torch CPU fp32 (ATen / oneDNN)"},
         "impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -1096,10 +1097,11 @@ def run_gpu_arm(args, dd):
     e2e_value = clips / (ms_e2e * 1e-3)
     d2h = GRID_POINTS * 8
     cfg = base_config(args.precision)
-    cfg.update({
+    cfg_detail = {}
+    cfg_detail.update({
         "arithmetic": "bf16x2-split operands (hi*hi+hi*lo+lo*hi on tcgen05), fp32 accumulate"
         if args.precision == "fp32" else "bf16 operands, fp32 accumulate",
-        "l2": "inputs larger than L2 (282 MB pyramid per step vs 126 MB L2)", "clips_per_step_per_gpu": 1,
+        "clips_per_step_per_gpu": 1,
         "host_pipelining": "submit()/result(): up to 2 steps in flight (two graph instances on two streams); the "
                            "result of step i is collected after step i+2 is enqueued",
         "parallelism": "clip-parallel x%d (no data-path collective in this line's `value`; the collective-bearing "
@@ -1109,7 +1111,7 @@ def run_gpu_arm(args, dd):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16",
-        "data": "synthetic", "config": cfg,
+        "data": "synthetic", "config": cfg, "config_detail": cfg_detail,
         "mvoxels_per_sec": value * VOXELS_PER_CLIP / 1e6,
         "grid_points_per_sec": value * GRID_POINTS,
         "clocks": clocks,

@@ -503,7 +503,8 @@ class DeviceStitcher(object):
             if cnt[idx] > 0:
                 counts[idx - 1] = cnt[idx]
                 spans[idx - 1] = [lo[idx], hi[idx]]
-        frame_labels = [self.frame_labels[t, :fcount[t]] if fcount[t] >= 0 else None for t in range(self.num_frames)]
+        container = self.frame_labels.clone()          # the stitcher may be reset and reused for the next video
+        frame_labels = [container[t, :fcount[t]] if fcount[t] >= 0 else None for t in range(self.num_frames)]
         out_labels, out_meta = [], []
         metas_host = torch.stack([m for _, _, _, m in self._subclips]).cpu().tolist() if self._subclips else []
         for i, (frames, labels, _, _) in enumerate(self._subclips):

@@ -172,6 +172,15 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
     meta_words = int(_lib.load().stemseg_seq_cluster_meta_words(e_dims, mi))
     hdr = max_t + 1 + meta_words
     with torch.cuda.device(dev):
+        # the stitcher (track container, statistics, workspace) is reused from video to video (same geometry)
+        cache_key = (num_frames, cap, max_local, max_t, hdr, world, n_sub, str(dev))
+        cached = getattr(pipeline, "_clip_parallel_cache", None)
+        if cached is None or cached[0] != cache_key:
+            cached = (cache_key, DeviceStitcher(num_frames, cap, dev, max_instances=mi, max_subclips=n_sub))
+            pipeline._clip_parallel_cache = cached
+        stitcher = cached[1]
+        stitcher.reset()
+        # fresh exchange buffers per video (caching allocator: no cudaMalloc): the returned per-sub-clip labels are views
         labels_buf = torch.empty((max_local, max_t * cap), dtype=torch.int64, device=dev)
         head_buf = torch.zeros((max_local, hdr), dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream(dev)
@@ -194,7 +203,6 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
             dist.all_gather_into_tensor(all_head, head_buf, group=group)
         else:
             all_labels, all_head = labels_buf.unsqueeze(0), head_buf.unsqueeze(0)
-        stitcher = DeviceStitcher(num_frames, cap, dev, max_instances=mi, max_subclips=n_sub)
         for i, frames in enumerate(subseq_frames):
             r, slot = i % world, i // world
             stitcher.add_subclip(frames, all_labels[r, slot], all_head[r, slot, :len(frames)],
