@@ -966,15 +966,18 @@ def run_gpu_arm(args, dd):
     # per-stage breakdown (untimed extra pass on rank 0; informational)
     stages = {}
     if rank == 0:
-        def ev_time(fn, reps=3):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
+        def ev_time(fn, reps=7):
+            """Median over `reps` synchronous calls, each bracketed by its own events (robust to a one-off hiccup)."""
+            times = []
             for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
                 out = fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps, out
+                b.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b))
+            return statistics.median(times), out
         emb, var, seedi, _ = pipe.run_heads(dev_feats)     # builds / warms the heads-only graph outside the timing
         pipe.cluster(emb, var, seedi, fg_mask)             # lazy kernel loading of the eager gather / cluster path
         stages["heads_ms"], (emb, var, seedi, _) = ev_time(lambda: pipe.run_heads(dev_feats))

@@ -42,14 +42,16 @@ def run(tr, n):
 
 
 results = {}
-for split in (False, True, False, True):
+for split in ((False, True, True) if os.environ.get("PROBE_SHORT") else (False, True, False, True)):
     tr = build(split)
     run(tr, 5)
     ms, _ = dd.timed(lambda: run(tr, 30))
     results.setdefault(split, []).append(ms / 30)
     if rank == 0:
-        print("world %d split_backward=%s: %.3f ms/step" % (world, split, ms / 30), flush=True)
-    if split and len(sys.argv) > 1 and sys.argv[1] == "timeline" and len(results[True]) == 2:
+        print("world %d split_backward=%s conv_smem_kb=%s nccl_max_nchannels=%s: %.3f ms/step" % (
+            world, split, os.environ.get("STEMSEG_CONV_SMEM_KB", "200"), os.environ.get("NCCL_MAX_NCHANNELS", "-"),
+            ms / 30), flush=True)
+    if split and len(sys.argv) > 1 and sys.argv[1] == "timeline" and len(results[True]) == (2 if not os.environ.get("PROBE_SHORT") else 2):
         from torch.profiler import ProfilerActivity, profile
         dd.barrier()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -59,7 +61,7 @@ for split in (False, True, False, True):
             evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
             evs.sort(key=lambda e: e.time_range.start)
             t0 = evs[0].time_range.start
-            with open("gpurun_out/train_timeline_n%d.txt" % world, "w") as f:
+            with open("gpurun_out/train_timeline_n%d.txt" % world, "w") as f:   # rank 0
                 for e in evs:
                     name = e.name.replace("void ", "").replace("stemseg::(anonymous namespace)::", "").split("(")[0][:70]
                     f.write("%9.1f %8.1f  %s\n" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, name))

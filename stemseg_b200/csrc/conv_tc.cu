@@ -20,6 +20,7 @@
 #include "trilinear.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 namespace stemseg {
@@ -842,15 +843,30 @@ int encode_weight_map(CUtensorMap* map, const void* base, int64_t k_total, int64
     return STEMSEG_OK;
 }
 
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudgetDefault = 200 * 1024;
 constexpr int kSmemLimit = 227 * 1024;
+
+// Shared memory the operand ring may take per CTA.  STEMSEG_CONV_SMEM_KB lowers it (e.g. 150) so that another resident
+// kernel's CTAs -- NCCL's all-reduce during the data-parallel backward pass -- fit next to a persistent conv CTA.
+int smem_budget() {
+    static int budget = -1;
+    if (budget < 0) {
+        budget = kSmemBudgetDefault;
+        const char* e = getenv("STEMSEG_CONV_SMEM_KB");
+        if (e != nullptr) {
+            const int kb = atoi(e);
+            if (kb >= 64 && kb <= 200) budget = kb * 1024;
+        }
+    }
+    return budget;
+}
 
 template <int BLOCK_N, int BLOCK_K, int PLANES>
 int launch_variant(const CUtensorMap* maps, ConvTcParams& p, int max_ctas, cudaStream_t stream) {
     constexpr int stage = stage_bytes<BLOCK_N, BLOCK_K, PLANES>();
     const int head_bytes = p.epi_mode == 1 ? static_cast<int>(align_up((p.head_j * BLOCK_N + p.head_j) * sizeof(float), 16)) : 0;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * BLOCK_N * 2 * 4 /*stat staging*/ + head_bytes;
-    int stages = (kSmemBudget - head_bytes - 4 * BLOCK_N * 2 * 4) / stage;
+    int stages = (smem_budget() - head_bytes - 4 * BLOCK_N * 2 * 4) / stage;
     if (stages * stage + fixed > kSmemLimit) stages = (kSmemLimit - fixed) / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2 || stages * stage + fixed > kSmemLimit) {
@@ -1117,7 +1133,7 @@ template <int BLOCK_N, int PLANES>
 int launch_wgrad(const CUtensorMap* maps, WgradParams& p, cudaStream_t stream) {
     constexpr int stage = PLANES * (2 + BLOCK_N / 64) * kWgBoxBytes;
     const int fixed = 1024 + 256;
-    int stages = (kSmemBudget) / stage;
+    int stages = smem_budget() / stage;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages * stage + fixed > kSmemLimit) stages = (kSmemLimit - fixed) / stage;
     if (stages < 2) {
