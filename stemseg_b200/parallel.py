@@ -184,18 +184,29 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
         labels_buf = torch.empty((max_local, max_t * cap), dtype=torch.int64, device=dev)
         head_buf = torch.zeros((max_local, hdr), dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream(dev)
+        # The copies into the exchange buffers run on their own stream: submit() makes the pipeline's stream wait for
+        # the CALLER's stream, so collecting sub-clip i on `main` would serialise sub-clip i+1 behind it and lose the
+        # two-steps-in-flight overlap.
+        collect = getattr(pipeline, "_collect_stream", None)
+        if collect is None or collect.device != dev:
+            collect = pipeline._collect_stream = torch.cuda.Stream(device=dev, priority=-1)
+        collect.wait_stream(main)                         # buffers above were allocated / zeroed on `main`
+        labels_buf.record_stream(collect)
+        head_buf.record_stream(collect)
         for slot, i in enumerate(shard_subclips(n_sub, rank, world)):
             frames = subseq_frames[i]
             pend = pipeline.submit(features_for_clip(i), fg_mask=masks[frames], cluster_label_start=1)
             view = pend.device_view()
-            main.wait_event(view["done"])
-            for key in ("labels", "counts", "meta"):        # allocated on the pipeline's stream, consumed on this one
-                view[key].record_stream(main)
+            collect.wait_event(view["done"])
             t_i = len(frames)
-            labels_buf[slot, :view["labels"].numel()].copy_(view["labels"], non_blocking=True)
-            head_buf[slot, :t_i].copy_(view["counts"][:t_i], non_blocking=True)
-            head_buf[slot, max_t:max_t + 1 + meta_words].copy_(
-                torch.cat([view["meta"][0:1], view["meta"]]), non_blocking=True)         # [K][meta words]
+            with torch.cuda.stream(collect):
+                for key in ("labels", "counts", "meta"):    # allocated on the pipeline's stream, consumed on this one
+                    view[key].record_stream(collect)
+                labels_buf[slot, :view["labels"].numel()].copy_(view["labels"], non_blocking=True)
+                head_buf[slot, :t_i].copy_(view["counts"][:t_i], non_blocking=True)
+                head_buf[slot, max_t:max_t + 1 + meta_words].copy_(
+                    torch.cat([view["meta"][0:1], view["meta"]]), non_blocking=True)     # [K][meta words]
+        main.wait_stream(collect)
         if world > 1:
             all_labels = torch.empty((world,) + tuple(labels_buf.shape), dtype=torch.int64, device=dev)
             all_head = torch.empty((world,) + tuple(head_buf.shape), dtype=torch.int32, device=dev)
