@@ -159,8 +159,8 @@ class SequentialClustering(ClustererBase):
         centers = floats[:mi * e].reshape(mi, e)[:k]
         bws = floats[mi * e:2 * mi * e].reshape(mi, e)[:k]
         unique_labels = [i + cluster_label_start for i in range(k)]                 # clusterers.py:121-123
-        label_centers = [c.tolist() for c in centers]                               # clusterers.py:124
-        label_stds = [(1. / b).clamp(min=1e-8).sqrt().tolist() for b in bws]        # clusterers.py:125
+        label_centers = centers.tolist()                                            # clusterers.py:124
+        label_stds = (1. / bws).clamp(min=1e-8).sqrt().tolist()                     # clusterers.py:125 (one op for all K)
         label_masks = []
         if return_label_masks:                                                      # clusterers.py:145-146
             label_masks = [(primary == i).cpu() for i in range(k)]

@@ -132,8 +132,8 @@ def _meta_dict(words, e, max_instances, offset_labels):
     floats = words[4 + max_instances:].view(torch.float32)
     centers = floats[:max_instances * e].reshape(max_instances, e)[:k]
     bws = floats[max_instances * e:2 * max_instances * e].reshape(max_instances, e)[:k]
-    return {"instance_labels": list(offset_labels), "instance_centers": [c.tolist() for c in centers],
-            "instance_stds": [(1. / b).clamp(min=1e-8).sqrt().tolist() for b in bws], "instance_masks": []}
+    return {"instance_labels": list(offset_labels), "instance_centers": centers.tolist(),
+            "instance_stds": (1. / bws).clamp(min=1e-8).sqrt().tolist(), "instance_masks": []}
 
 
 @torch.no_grad()
