@@ -287,34 +287,38 @@ __global__ void __launch_bounds__(kAssignThreads) stitch_assign_kernel(const Sti
         }
     }
     __syncthreads();
-    if (associate && tid == 0) {
-        long long vals1[kAssocMaxSide + 1], vals2[kAssocMaxSide + 1];
-        int n1 = 0, n2 = 0, err = 0;
-        // labels present in the overlap frames, ascending like Tensor.unique(), outliers (-1) first
-        for (int g = 0; g <= highest0 && g <= a.max_labels; ++g)
-            if (sm.size_a[g] > 0) {
-                if (n1 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
-                vals1[n1++] = g == 0 ? -1 : g;
-            }
-        for (int l = 0; l <= k && l < kAssocMaxSide + 2; ++l)
-            if (sm.size_b[l] > 0) {
-                if (n2 >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
-                vals2[n2++] = l == 0 ? -1 : offset + l;
-            }
-        if (!err) {
-            const int c1 = pyset_order(vals1, n1, sm.u1);
-            const int c2 = pyset_order(vals2, n2, sm.u2);
-            if (c1 < 0 || c2 < 0) err |= kErrTooManyLabels;
-            else {
-                // every current label is > every existing one (offset = next_track_label - 1 >= highest existing label)
-                for (int i = 0; i < c1; ++i)
-                    if (sm.u1[i] > offset) err |= kErrLabelsOverlap;
-                sm.c1 = c1;
-                sm.c2 = c2;
-            }
+    // the two label lists are ordered independently: thread 0 takes the existing ids, thread 32 (another warp) the
+    // current ones -- each emulation is a chain of dependent table probes, so running them side by side halves it
+    if (associate && (tid == 0 || tid == 32)) {
+        long long vals[kAssocMaxSide + 1];
+        int n = 0, err = 0;
+        if (tid == 0) {      // ids present in the overlap frames, ascending like Tensor.unique(), outliers (-1) first
+            for (int g = 0; g <= highest0 && g <= a.max_labels; ++g)
+                if (sm.size_a[g] > 0) {
+                    if (n >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
+                    vals[n++] = g == 0 ? -1 : g;
+                }
+        } else {
+            for (int l = 0; l <= k && l < kAssocMaxSide + 2; ++l)
+                if (sm.size_b[l] > 0) {
+                    if (n >= kAssocMaxSide) { err |= kErrTooManyLabels; break; }
+                    vals[n++] = l == 0 ? -1 : offset + l;
+                }
         }
-        if (err) { sm.err |= err; sm.c1 = sm.c2 = 0; }
+        int c = 0;
+        if (!err) {
+            c = pyset_order(vals, n, tid == 0 ? sm.u1 : sm.u2);
+            if (c < 0) { err |= kErrTooManyLabels; c = 0; }
+            // every current label is > every existing one (offset = next_track_label - 1 >= highest existing label)
+            if (tid == 0)
+                for (int i = 0; i < c; ++i)
+                    if (sm.u1[i] > offset) err |= kErrLabelsOverlap;
+        }
+        if (tid == 0) sm.c1 = c; else sm.c2 = c;
+        if (err) atomicOr(&sm.err, err);
     }
+    __syncthreads();
+    if (tid == 0 && sm.err) sm.c1 = sm.c2 = 0;
     __syncthreads();
     const int c1 = sm.c1, c2 = sm.c2;
     for (int idx = tid; idx < c1 * c2; idx += kAssignThreads) {

@@ -146,7 +146,7 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
 
     Nothing is synchronised with the host until the whole video is stitched: every owned sub-clip is enqueued
     (``submit``), its local labels / per-frame counts / clustering meta words are copied device-to-device into two
-    fixed-layout exchange buffers, ONE all_gather per buffer (NCCL) makes every sub-clip visible on every rank, and the
+    ONE fixed-layout exchange buffer, a single all_gather (NCCL) makes every sub-clip visible on every rank, and the
     sequential stitch runs on the device (``DeviceStitcher``: histogram -> assignment -> relabel kernels per sub-clip).
     The only device->host copy is the final one in ``DeviceStitcher.finish``."""
     from stemseg_b200.chaining import DeviceStitcher
@@ -181,8 +181,12 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
         stitcher = cached[1]
         stitcher.reset()
         # fresh exchange buffers per video (caching allocator: no cudaMalloc): the returned per-sub-clip labels are views
-        labels_buf = torch.empty((max_local, max_t * cap), dtype=torch.int64, device=dev)
-        head_buf = torch.zeros((max_local, hdr), dtype=torch.int32, device=dev)
+        # ONE exchange buffer: [labels int64 x T*h*w | header int32 x hdr (in int64 slots)] per owned sub-clip
+        hdr64 = (hdr + 1) // 2
+        row = max_t * cap + hdr64
+        xbuf = torch.zeros((max_local, row), dtype=torch.int64, device=dev)
+        labels_buf = xbuf[:, :max_t * cap]
+        head_buf = xbuf[:, max_t * cap:].view(torch.int32)[:, :hdr]
         main = torch.cuda.current_stream(dev)
         # The copies into the exchange buffers run on their own stream: submit() makes the pipeline's stream wait for
         # the CALLER's stream, so collecting sub-clip i on `main` would serialise sub-clip i+1 behind it and lose the
@@ -191,8 +195,7 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
         if collect is None or collect.device != dev:
             collect = pipeline._collect_stream = torch.cuda.Stream(device=dev, priority=-1)
         collect.wait_stream(main)                         # buffers above were allocated / zeroed on `main`
-        labels_buf.record_stream(collect)
-        head_buf.record_stream(collect)
+        xbuf.record_stream(collect)
         for slot, i in enumerate(shard_subclips(n_sub, rank, world)):
             frames = subseq_frames[i]
             pend = pipeline.submit(features_for_clip(i), fg_mask=masks[frames], cluster_label_start=1)
@@ -208,12 +211,12 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
                     torch.cat([view["meta"][0:1], view["meta"]]), non_blocking=True)     # [K][meta words]
         main.wait_stream(collect)
         if world > 1:
-            all_labels = torch.empty((world,) + tuple(labels_buf.shape), dtype=torch.int64, device=dev)
-            all_head = torch.empty((world,) + tuple(head_buf.shape), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(all_labels, labels_buf, group=group)
-            dist.all_gather_into_tensor(all_head, head_buf, group=group)
+            gathered = torch.empty((world, max_local, row), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, xbuf, group=group)
         else:
-            all_labels, all_head = labels_buf.unsqueeze(0), head_buf.unsqueeze(0)
+            gathered = xbuf.unsqueeze(0)
+        all_labels = gathered[:, :, :max_t * cap]
+        all_head = gathered[:, :, max_t * cap:].view(torch.int32)[:, :, :hdr]
         for i, frames in enumerate(subseq_frames):
             r, slot = i % world, i // world
             stitcher.add_subclip(frames, all_labels[r, slot], all_head[r, slot, :len(frames)],
