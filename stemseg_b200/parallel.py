@@ -145,7 +145,7 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
     features_for_clip(i) -> {scale: tensor} pyramid of sub-clip i (only called for owned sub-clips).
 
     Nothing is synchronised with the host until the whole video is stitched: every owned sub-clip is enqueued
-    (``submit``), its local labels / per-frame counts / clustering meta words are copied device-to-device into two
+    (``submit``), its local labels / per-frame counts / clustering meta words are copied device-to-device into
     ONE fixed-layout exchange buffer, a single all_gather (NCCL) makes every sub-clip visible on every rank, and the
     sequential stitch runs on the device (``DeviceStitcher``: histogram -> assignment -> relabel kernels per sub-clip).
     The only device->host copy is the final one in ``DeviceStitcher.finish``."""
