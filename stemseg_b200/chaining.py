@@ -8,6 +8,11 @@ The per-point work of ``cluster_subsequence`` (gather + clustering) runs in the 
 (``stitch_subsequences``) is integer host logic on label vectors: a K1 x K2 (<= 20 x 20) IoU table from one joint
 histogram per overlap and scipy's Hungarian solver, exactly like online_chainer.py:291-343.  It only consumes
 labels, which is what makes sub-clips independent and the path clip-parallel (stemseg_b200/parallel.py).
+
+``TrackContainer`` and ``get_subsequence_frames`` are host control-plane mirrors of the reference classes (same method
+names, assertions and return values, because ``OnlineChainer.process`` callers and the output generators index into
+them); they hold no per-point arithmetic.  The device-resident equivalent used on the fast path is ``DeviceStitcher``
+(csrc/stitch.cu), which keeps the same state in GPU memory.
 """
 from collections import defaultdict
 
