@@ -125,6 +125,49 @@ def exchange_and_stitch_device(num_frames, subseq_frames, local_results, group=N
     return stitch_subsequences_device(num_frames, subseq_frames, labels, counts, ks, metas)
 
 
+class ExchangeLayout(object):
+    """Fixed layout of the ONE buffer every rank contributes to the all_gather: per owned sub-clip a row of int64 slots
+    ``[labels: max_t * cap | header]`` whose header holds int32 words ``[per-frame counts: max_t | K | clustering meta]``.
+    Nothing is pickled and nothing depends on data-dependent sizes, so the exchange needs no host round trip."""
+
+    def __init__(self, n_sub, world, max_t, cap, meta_words):
+        self.n_sub, self.world, self.max_t, self.cap, self.meta_words = n_sub, world, max_t, cap, meta_words
+        self.max_local = (n_sub + world - 1) // world
+        self.label_slots = max_t * cap
+        self.hdr = max_t + 1 + meta_words
+        self.row = self.label_slots + (self.hdr + 1) // 2
+
+    def alloc(self, device):
+        return torch.zeros((self.max_local, self.row), dtype=torch.int64, device=device)
+
+    def views(self, buf):
+        """buf [..., row] int64 -> (labels [..., max_t*cap] int64, header [..., hdr] int32), both views of `buf`."""
+        labels = buf[..., :self.label_slots]
+        head = buf[..., self.label_slots:].view(torch.int32)[..., :self.hdr]
+        return labels, head
+
+    def slot_of(self, i):
+        """Sub-clip i lives in row `slot` of rank `r` (round-robin ownership, shard_subclips)."""
+        return i % self.world, i // self.world
+
+    def write(self, buf, slot, labels, counts, meta):
+        """Fill one row: local labels (any length <= max_t*cap), per-frame counts (int32 [t]), clustering meta words."""
+        lab, head = self.views(buf)
+        lab[slot, :labels.numel()].copy_(labels, non_blocking=True)
+        t = counts.numel()
+        head[slot, :t].copy_(counts, non_blocking=True)
+        head[slot, self.max_t:self.max_t + 1 + self.meta_words].copy_(torch.cat([meta[0:1], meta]), non_blocking=True)
+
+    def gather(self, buf, group=None):
+        """All ranks' buffers [world, max_local, row] (the input itself, unsqueezed, for a single process)."""
+        if self.world == 1:
+            return buf.unsqueeze(0)
+        # concatenation along dim 0 (the form every backend accepts), viewed per rank
+        out = torch.empty((self.world * buf.shape[0],) + tuple(buf.shape[1:]), dtype=torch.int64, device=buf.device)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        return out.view((self.world,) + tuple(buf.shape))
+
+
 def _meta_dict(words, e, max_instances, offset_labels):
     """Clustering meta words (host int32 tensor) -> the reference's meta dict (clusterers.py:161-166) with the given
     (already stitched) instance labels."""
@@ -165,67 +208,51 @@ def clip_parallel_process(pipeline, masks, subseq_frames, features_for_clip, gro
     num_frames = max(max(f) for f in subseq_frames) + 1
     max_t = max(len(f) for f in subseq_frames)
     cap = int(masks.shape[-2]) * int(masks.shape[-1])
-    max_local = (n_sub + world - 1) // world
     mi = pipeline.clusterer.max_instances
     e_dims = pipeline.embedding_head.embedding_size
     from stemseg_b200 import _lib
     meta_words = int(_lib.load().stemseg_seq_cluster_meta_words(e_dims, mi))
-    hdr = max_t + 1 + meta_words
+    layout = ExchangeLayout(n_sub, world, max_t, cap, meta_words)
     with torch.cuda.device(dev):
         # the stitcher (track container, statistics, workspace) is reused from video to video (same geometry)
-        cache_key = (num_frames, cap, max_local, max_t, hdr, world, n_sub, str(dev))
+        cache_key = (num_frames, cap, layout.max_local, max_t, layout.hdr, world, n_sub, str(dev))
         cached = getattr(pipeline, "_clip_parallel_cache", None)
         if cached is None or cached[0] != cache_key:
             cached = (cache_key, DeviceStitcher(num_frames, cap, dev, max_instances=mi, max_subclips=n_sub))
             pipeline._clip_parallel_cache = cached
         stitcher = cached[1]
         stitcher.reset()
-        # fresh exchange buffers per video (caching allocator: no cudaMalloc): the returned per-sub-clip labels are views
-        # ONE exchange buffer: [labels int64 x T*h*w | header int32 x hdr (in int64 slots)] per owned sub-clip
-        hdr64 = (hdr + 1) // 2
-        row = max_t * cap + hdr64
-        xbuf = torch.zeros((max_local, row), dtype=torch.int64, device=dev)
-        labels_buf = xbuf[:, :max_t * cap]
-        head_buf = xbuf[:, max_t * cap:].view(torch.int32)[:, :hdr]
+        # a fresh exchange buffer per video (caching allocator: no cudaMalloc): the returned per-sub-clip labels are views
+        xbuf = layout.alloc(dev)
         main = torch.cuda.current_stream(dev)
-        # The copies into the exchange buffers run on their own stream: submit() makes the pipeline's stream wait for
+        # The copies into the exchange buffer run on their own stream: submit() makes the pipeline's stream wait for
         # the CALLER's stream, so collecting sub-clip i on `main` would serialise sub-clip i+1 behind it and lose the
         # two-steps-in-flight overlap.
         collect = getattr(pipeline, "_collect_stream", None)
         if collect is None or collect.device != dev:
             collect = pipeline._collect_stream = torch.cuda.Stream(device=dev, priority=-1)
-        collect.wait_stream(main)                         # buffers above were allocated / zeroed on `main`
+        collect.wait_stream(main)                         # the buffer above was allocated / zeroed on `main`
         xbuf.record_stream(collect)
         for slot, i in enumerate(shard_subclips(n_sub, rank, world)):
             frames = subseq_frames[i]
             pend = pipeline.submit(features_for_clip(i), fg_mask=masks[frames], cluster_label_start=1)
             view = pend.device_view()
             collect.wait_event(view["done"])
-            t_i = len(frames)
             with torch.cuda.stream(collect):
                 for key in ("labels", "counts", "meta"):    # allocated on the pipeline's stream, consumed on this one
                     view[key].record_stream(collect)
-                labels_buf[slot, :view["labels"].numel()].copy_(view["labels"], non_blocking=True)
-                head_buf[slot, :t_i].copy_(view["counts"][:t_i], non_blocking=True)
-                head_buf[slot, max_t:max_t + 1 + meta_words].copy_(
-                    torch.cat([view["meta"][0:1], view["meta"]]), non_blocking=True)     # [K][meta words]
+                layout.write(xbuf, slot, view["labels"], view["counts"][:len(frames)], view["meta"])
         main.wait_stream(collect)
-        if world > 1:
-            gathered = torch.empty((world, max_local, row), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered, xbuf, group=group)
-        else:
-            gathered = xbuf.unsqueeze(0)
-        all_labels = gathered[:, :, :max_t * cap]
-        all_head = gathered[:, :, max_t * cap:].view(torch.int32)[:, :, :hdr]
+        all_labels, all_head = layout.views(layout.gather(xbuf, group=group))
         for i, frames in enumerate(subseq_frames):
-            r, slot = i % world, i // world
+            r, slot = layout.slot_of(i)
             stitcher.add_subclip(frames, all_labels[r, slot], all_head[r, slot, :len(frames)],
                                  all_head[r, slot, max_t:max_t + 1])
         head_host = all_head.cpu()                      # stream-ordered after the stitch kernels: the video's one sync
         container, out_labels, out_meta = stitcher.finish()
     metas = []
     for i in range(n_sub):
-        r, slot = i % world, i // world
+        r, slot = layout.slot_of(i)
         metas.append(_meta_dict(head_host[r, slot, max_t + 1:], e_dims, mi, out_meta[i]["instance_labels"]))
     return container, out_labels, metas
 
