@@ -208,6 +208,9 @@ def run_reference_arm(args, rank, world):
 class ClockSampler(object):
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    # 100 ms is deliberate: every nvidia-smi sample takes driver locks.  A/B on a B200 (3 runs each): 100 ms -> 2.73-2.85
+    # ms/step; 20 ms -> one of three runs at 15.6 ms/step (launches stalled behind NVML queries).
+    PERIOD_MS = int(os.environ.get("STEMSEG_BENCH_CLOCK_MS", "100"))
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
@@ -220,7 +223,7 @@ class ClockSampler(object):
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--id=%d" % self.gpu_index, "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", str(self.PERIOD_MS)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
             # wait for the first sample: NVML initialisation takes 0.1-0.3 s and holds driver locks that stall CUDA
             # launches of this process for tens of ms -- inside a 55 ms timed region that is +1.5 ms per step (seen as
             # 4.32 instead of 2.77 ms/step in two of ten runs).  Sampling then continues through the timed region.
